@@ -1,0 +1,143 @@
+/* valley_b200.h -- C ABI of libvalley_b200.so: the B200-native (sm_100a) implementation of Valley's
+ * multimodal forward hot path (CLIP ViT-L/14 encode -> temporal pool + mm_projector -> LLaMA decoder
+ * with KV cache -> greedy token).
+ *
+ * The reference (RupertLuo/Valley) has NO FFI / plugin interface: the boundary it offers is the Python
+ * nn.Module surface of valley/model/valley_model.py, whose arithmetic is delegated to HuggingFace
+ * transformers + ATen.  Each entry point below therefore cites the Python code path it stands in for;
+ * valley_b200/model.py re-exposes them under the reference's own class/method names.
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw device pointers + explicit sizes, no C++/torch types.
+ *   - every call returns VLY_OK (0) or a negative vly_status; vly_last_error() gives a thread-local message.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. a torch tensor's data_ptr());
+ *     the library owns only its packed weights, workspace and KV caches (tied to vly_ctx / vly_kv).
+ *   - calls are stream-ordered on the cudaStream_t passed in (void* stream; NULL = legacy default stream).
+ *   - there is NO CPU fallback: without a CUDA device of compute capability 10.x vly_create fails.
+ *   - hot calls do not allocate once the workspace has grown to the largest shapes seen, so the decode
+ *     step is captured in a CUDA graph (vly_generate_greedy).
+ *   - thread safety: a vly_ctx serialises its workspace-using calls with an internal mutex
+ *     (model_worker.py:467-474 may call the model from up to 5 threads); distinct vly_kv are independent.
+ */
+#ifndef VALLEY_B200_H_
+#define VALLEY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vly_ctx vly_ctx;
+typedef struct vly_kv vly_kv;
+
+typedef enum {
+  VLY_OK = 0,
+  VLY_ERR_INVALID = -1,          /* bad argument / shape                                          */
+  VLY_ERR_CUDA = -2,             /* CUDA runtime / driver failure                                  */
+  VLY_ERR_STATE = -3,            /* call order violated (e.g. weights not finalised)               */
+  VLY_ERR_IM_COUNT = -10,        /* "The number of im_start_token and im_end_token should be the same" (valley_model.py:219-220) */
+  VLY_ERR_IM_CUT = -11,          /* "Seems that the image is cut." (valley_model.py:226-227)       */
+  VLY_ERR_INDEX = -12            /* IndexError the reference would raise reading past the ids row  */
+} vly_status;
+
+typedef enum { VLY_F32 = 0, VLY_BF16 = 1, VLY_F16 = 2 } vly_dtype;
+
+/* ValleyConfig(LlamaConfig) keys + the CLIPVisionConfig of config.mm_vision_tower (valley_model.py:18-56). */
+typedef struct {
+  int32_t hidden_size, num_hidden_layers, num_attention_heads, intermediate_size, vocab_size;
+  float rms_norm_eps, rope_theta;
+  int32_t max_position_embeddings;   /* KV-cache capacity per sequence (model_max_length 2048, valley_stage2.yaml:54) */
+  int32_t vit_hidden, vit_layers, vit_heads, vit_mlp, vit_patch, vit_image;
+  float vit_eps;
+  int32_t mm_vision_select_layer;    /* config.mm_vision_select_layer (default -1, yaml -2; valley_model.py:173) */
+  int32_t device;                    /* CUDA device ordinal */
+} vly_config;
+
+/* Sentinel token ids kept on vision_tower.config by every entry point (run_valley.py:13-18). -1 = unset. */
+typedef struct {
+  int64_t im_patch_token, im_start_token, im_end_token, vi_frame_token, vi_start_token, vi_end_token;
+} vly_tokens;
+
+const char* vly_last_error(void);
+const char* vly_version(void);
+
+/* ---- lifetime ---- replaces ValleyLlamaForCausalLM.from_pretrained / __init__ (valley_model.py:24-56, :260-267) */
+int vly_create(const vly_config* cfg, vly_ctx** out);
+void vly_destroy(vly_ctx* ctx);
+
+/* ---- weights ---- accepts HF state_dict names: model.embed_tokens.weight, model.layers.{i}.*,
+ * model.norm.weight, lm_head.weight, model.mm_projector.{weight,bias}, model.vision_tower.vision_model.*
+ * Data is copied (converted to bf16) immediately; vly_finalize_weights packs the kernel layouts
+ * (fused QKV, LayerNorm/RMSNorm gamma folded into the following Linear, RoPE pair interleave,
+ * gate/up interleave) and frees the staging copies. */
+int vly_load_weight(vly_ctx* ctx, const char* hf_name, const void* dev_ptr, int dtype, const int64_t* shape, int ndim);
+int vly_finalize_weights(vly_ctx* ctx);
+
+/* ---- vision tower ---- vision_tower(images, output_hidden_states=True).hidden_states[select_layer]
+ * (valley_model.py:172-184; HF modeling_clip.py:202-219, :363-385, :667-690).
+ * pixels [F,3,224,224] of pixel_dtype -> out [F,257,1024] bf16.  Only the layers needed are run. */
+int vly_vit_encode(vly_ctx* ctx, const void* pixels_dev, int pixel_dtype, int n_frames, int select_layer, void* out_dev,
+                   void* stream);
+
+/* ---- mm_projector over every token, == encode_images' projection (valley_model.py:187-190):
+ * feats [rows,1024] bf16 -> out [rows,hidden] bf16 */
+int vly_project(vly_ctx* ctx, const void* feats_dev, int64_t rows, void* out_dev, void* stream);
+
+/* ---- temporal mean pool + projector, pool-first (valley_model.py:207, :215 + :190):
+ * feats [n_videos*T,257,1024] bf16 -> vis_rows [n_videos, 256+T, hidden] bf16
+ * (rows 0..255 = projected mean patch features, rows 256.. = projected per-frame CLS features) */
+int vly_pool_project(vly_ctx* ctx, const void* feats_dev, int n_videos, int T, void* vis_rows_dev, void* stream);
+
+/* ---- splice plan (pure host integer logic, exact; valley_model.py:196-246).  ids_host [B,S] int64.
+ * src_map_host [B,S] int32: -1 = keep the token embedding, j in [0,256) = pooled row j, 256+t = frame t's CLS row.
+ * img_idx_host [B] int32: which entry of image_features the sample consumes (-1 = not multimodal).
+ * Returns VLY_OK or VLY_ERR_IM_COUNT / VLY_ERR_IM_CUT / VLY_ERR_INDEX exactly where the reference raises.  Needs no GPU. */
+int vly_build_splice_map(const int64_t* ids_host, int B, int S, int T, const vly_tokens* tok, int32_t* src_map_host,
+                         int32_t* img_idx_host);
+
+/* ---- embed_tokens gather + splice (valley_model.py:160, :223-247): -> inputs_embeds [B,S,hidden] bf16 */
+int vly_embed_splice(vly_ctx* ctx, const int64_t* ids_dev, const int32_t* src_map_dev, const int32_t* img_idx_dev,
+                     const void* vis_rows_dev, int rows_per_img, int B, int S, void* inputs_embeds_dev, void* stream);
+
+/* ---- KV cache ---- replaces HF DynamicCache / the tuple cache (cache_utils.py:102-120): pre-allocated
+ * [L][2][B][heads][max_seq][128] bf16, appended in place by the QKV epilogues. */
+int vly_kv_create(vly_ctx* ctx, int batch, int max_seq, vly_kv** out);
+void vly_kv_destroy(vly_kv* kv);
+int vly_kv_seq_len(vly_kv* kv, int* out_len);   /* host-visible length (syncs the kv's stream state) */
+int vly_kv_reset(vly_kv* kv, void* stream);
+/* copy layer l's K (which=0) or V (which=1) as HF-layout [B,heads,len,128] bf16 (de-interleaves K) -- for tests/drop-in */
+int vly_kv_export(vly_ctx* ctx, vly_kv* kv, int layer, int which, void* out_dev, void* stream);
+
+/* ---- LlamaModel.forward + lm_head on S new positions (valley_model.py:249-254, :304-305;
+ * HF modeling_llama.py:375-426).  inputs_embeds [B,S,hidden] bf16.
+ * logits_mode 0: none; 1: last position only -> logits_dev [B,V] fp32; 2: all positions -> [B,S,V] fp32.
+ * hidden_out_dev (optional) receives the final-norm'ed hidden states is NOT provided: norm is folded into lm_head. */
+int vly_llama_prefill(vly_ctx* ctx, vly_kv* kv, const void* inputs_embeds_dev, int B, int S, int logits_mode,
+                      void* logits_dev, int64_t* next_tokens_dev, void* stream);
+
+/* ---- one decode step for B sequences (model_worker.py:380-391): tokens_dev [B] int64 -> next_tokens_dev [B]
+ * int64 = argmax (lowest index on ties); logits_dev optional [B,V] fp32. */
+int vly_llama_decode(vly_ctx* ctx, vly_kv* kv, const int64_t* tokens_dev, int64_t* next_tokens_dev, void* logits_dev,
+                     void* stream);
+
+/* ---- n_steps greedy decode steps with no host round trip (CUDA graph replay): first_tokens_dev [B] is fed at step 0,
+ * step i's argmax is fed to step i+1; out_tokens_dev [B, n_steps] int64 receives every argmax. */
+int vly_generate_greedy(vly_ctx* ctx, vly_kv* kv, const int64_t* first_tokens_dev, int n_steps, int64_t* out_tokens_dev,
+                        void* stream);
+
+/* ---- introspection for bench / tests ---- */
+int vly_kernel_launch_count(vly_ctx* ctx, int64_t* out);   /* kernels launched by this ctx so far */
+int vly_num_sms(vly_ctx* ctx, int* out);
+
+/* ---- low-level op hooks (per-kernel parity tests) ----
+ * D[M,N] = epilogue(A[M,K] * W[N,K]^T): epi 0 bias->bf16, 3 bias+residual (in-place allowed)->bf16.  bias_dev fp32 or NULL. */
+int vly_test_gemm(vly_ctx* ctx, const void* a_dev, const void* w_dev, int M, int N, int K, int epi, const float* bias_dev,
+                  const void* residual_dev, void* out_dev, int block_n, void* stream);
+/* ViT attention on a packed qkv [F*257, 3072] bf16 -> ctx [F*257,1024] bf16 */
+int vly_test_vit_attention(vly_ctx* ctx, const void* qkv_dev, int n_frames, void* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VALLEY_B200_H_ */

@@ -1,0 +1,1110 @@
+// libvalley_b200.so -- host side of the C ABI declared in include/valley_b200.h.
+// Owns: packed weights, workspace, KV caches, CUDA-graph of the decode step.  No torch, no CPU fallback.
+#include <cuda_runtime.h>
+#include <cuda.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/valley_b200.h"
+#include "attention_tc.cuh"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "simt_kernels.cuh"
+
+using namespace vly;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+extern "C" void vly_set_error_(const char* m) { snprintf(g_err, sizeof(g_err), "%s", m); }
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char* vly_last_error(void) { return g_err; }
+extern "C" const char* vly_version(void) { return "valley_b200 0.1 (sm_100a)"; }
+
+#define CK(expr)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess) return fail(VLY_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+  } while (0)
+#define CKL() CK(cudaGetLastError())
+#define TRY(expr)              \
+  do {                         \
+    int r_ = (expr);           \
+    if (r_ != VLY_OK) return r_; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// data structures
+// ------------------------------------------------------------------------------------------------
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+static int ensure(Buf& b, size_t bytes) {
+  if (b.bytes >= bytes) return VLY_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.bytes = 0;
+  CK(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return VLY_OK;
+}
+
+struct Staged {
+  std::vector<int64_t> shape;
+  void* dev = nullptr;
+  bool is_f32 = false;  // vectors are kept as fp32 holding bf16-rounded values; matrices as bf16
+  int64_t numel = 0;
+};
+
+struct VitLayerW {
+  bf16 *wqkv, *wo, *w1, *w2;
+  float *qkv_cs, *qkv_b, *bo, *c1, *b1, *b2;
+};
+struct LlamaLayerW {
+  bf16 *wqkv, *wo, *wgu, *wdown;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct vly_ctx {
+  vly_config cfg;
+  int num_sms = 148;
+  PFN_encodeTiled encode = nullptr;
+  std::mutex mu;
+  std::map<std::string, Staged> staged;
+  bool finalized = false;
+  bool has_vit = false, has_llm = false;
+  std::vector<void*> owned;  // every packed weight allocation
+  // ViT
+  int kpad = 0;
+  bf16* patch_w = nullptr;
+  float *cls = nullptr, *pos = nullptr, *pre_g = nullptr, *pre_b = nullptr;
+  std::vector<VitLayerW> vit;
+  bf16* proj_w = nullptr;
+  float* proj_b = nullptr;
+  // LLaMA
+  bf16* embed = nullptr;
+  std::vector<LlamaLayerW> layers;
+  bf16* lm_head = nullptr;
+  float2* rope = nullptr;
+  // workspace
+  Buf w_col, w_patch, w_qkv, w_ctx, w_h, w_stats, w_pool, w_x, w_q, w_attn, w_hb, w_pstats;
+  cudaStream_t cap_stream = nullptr;
+  int64_t launches = 0;
+};
+
+struct vly_kv {
+  vly_ctx* ctx;
+  int B, Smax;
+  bf16* cache = nullptr;  // [L][2][B][nH][Smax][128]
+  int host_len = 0;
+  int* d_len = nullptr;   // device scalar
+  int* d_step = nullptr;
+  // decode workspace
+  bf16 *x = nullptr, *q = nullptr, *attn = nullptr, *hb = nullptr;
+  float* part_o = nullptr;
+  float2* part_ml = nullptr;
+  unsigned int* counters = nullptr;   // [B*nH] + 1 (argmax)
+  float* part_val = nullptr;
+  int* part_idx = nullptr;
+  float* logits = nullptr;            // [B, V]
+  long long* cur_tokens = nullptr;    // [B]
+  long long* gen_tokens = nullptr;    // [B, Smax]
+  int nsplit = 1, gemv_grid = 0;
+  cudaGraphExec_t graph = nullptr;
+  int graph_nodes = 0;
+  size_t layer_stride() const { return (size_t)2 * B * ctx->cfg.num_attention_heads * Smax * 128; }
+  bf16* k_layer(int l) const { return cache + (size_t)l * layer_stride(); }
+  bf16* v_layer(int l) const { return k_layer(l) + layer_stride() / 2; }
+};
+
+static inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors
+// ------------------------------------------------------------------------------------------------
+static int make_tmap_2d(vly_ctx* c, CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_rows) {
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VLY_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d (ptr=%p inner=%llu rows=%llu stride=%llu box=%u,%u)", (int)r, ptr,
+                (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_inner, box_rows);
+  return VLY_OK;
+}
+static int make_tmap_3d(vly_ctx* c, CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                        uint32_t b0, uint32_t b1) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VLY_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launcher
+// ------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W, long long ldw, GemmParams p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ta, tb;
+  TRY(make_tmap_2d(c, &ta, A, p.K, p.M, lda * 2, 64, 128));
+  TRY(make_tmap_2d(c, &tb, W, p.K, p.N, ldw * 2, 64, BN));
+  p.num_m_tiles = cdiv(p.M, 128);
+  p.num_n_tiles = cdiv(p.N, BN);
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+  gemm_tc_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+template <int EPI>
+static int launch_gemm(vly_ctx* c, int bn, const bf16* A, long long lda, const bf16* W, long long ldw, const GemmParams& p,
+                       cudaStream_t st) {
+  if (bn == 256) return launch_gemm_t<256, EPI>(c, A, lda, W, ldw, p, st);
+  return launch_gemm_t<128, EPI>(c, A, lda, W, ldw, p, st);
+}
+static inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
+
+// ------------------------------------------------------------------------------------------------
+// weight packing kernels
+// ------------------------------------------------------------------------------------------------
+// One CTA per SOURCE row r.  dst row: mode 0 -> off + r; mode 1 (RoPE pair interleave inside 128-wide heads) ->
+// off + h*128 + (d < 64 ? 2d : 2(d-64)+1); mode 2 (gate/up interleave) -> 2r + off.
+__global__ void pack_rows_kernel(const bf16* __restrict__ src, int K, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ bias_in, bf16* __restrict__ dst, int Kdst, int mode, int off,
+                                 float* __restrict__ colsum, float* __restrict__ bias_out) {
+  __shared__ float r1[8], r2[8];
+  const int r = blockIdx.x;
+  int dr;
+  if (mode == 0) dr = off + r;
+  else if (mode == 1) {
+    const int h = r >> 7, d = r & 127;
+    dr = off + h * 128 + (d < 64 ? 2 * d : 2 * (d - 64) + 1);
+  } else dr = 2 * r + off;
+  float cs = 0.f, bb = 0.f;
+  for (int k = threadIdx.x; k < Kdst; k += blockDim.x) {
+    float wf = 0.f;
+    if (k < K) {
+      const float w = __bfloat162float(src[(size_t)r * K + k]);
+      wf = gamma ? bf16_round(w * gamma[k]) : w;
+      if (beta) bb += w * beta[k];
+    }
+    dst[(size_t)dr * Kdst + k] = __float2bfloat16_rn(wf);
+    cs += wf;
+  }
+  cs = warp_sum(cs);
+  bb = warp_sum(bb);
+  if ((threadIdx.x & 31) == 0) {
+    r1[threadIdx.x >> 5] = cs;
+    r2[threadIdx.x >> 5] = bb;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      a += r1[i];
+      b += r2[i];
+    }
+    if (colsum) colsum[dr] = a;
+    if (bias_out) bias_out[dr] = (bias_in ? bias_in[r] : 0.f) + b;
+  }
+}
+
+// rope[pos, j] = (cos, sin) of pos * theta^(-2j/128), computed in fp32 like HF (modeling_llama.py:124-135) and rounded
+// to bf16 (cos.to(x.dtype)).
+__global__ void rope_table_kernel(float2* rope, int max_pos, float theta, int head_dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = head_dim / 2;
+  if (i >= max_pos * half) return;
+  const int pos = i / half, j = i % half;
+  const float inv = 1.0f / powf(theta, float(2 * j) / float(head_dim));
+  const float fr = float(pos) * inv;
+  rope[i] = make_float2(bf16_round(cosf(fr)), bf16_round(sinf(fr)));
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+// inputs_embeds -> x (copy) + row statistics
+__global__ void __launch_bounds__(128) copy_rows_stats_kernel(const bf16* __restrict__ in, bf16* __restrict__ out,
+                                                              float2* __restrict__ stats, int stats_nt, int H) {
+  __shared__ float red[4];
+  const int row = blockIdx.x;
+  float s = 0.f, sq = 0.f;
+  for (int c = threadIdx.x * 8; c < H; c += 128 * 8) {
+    const uint4 w = *reinterpret_cast<const uint4*>(in + (size_t)row * H + c);
+    *reinterpret_cast<uint4*>(out + (size_t)row * H + c) = w;
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = bf16_lo(ww[i]), b = bf16_hi(ww[i]);
+      s += a + b;
+      sq += a * a + b * b;
+    }
+  }
+  s = block_sum_128(s, red);
+  sq = block_sum_128(sq, red);
+  if (threadIdx.x < stats_nt) stats[(size_t)row * stats_nt + threadIdx.x] = threadIdx.x == 0 ? make_float2(s, sq) : make_float2(0.f, 0.f);
+}
+
+// cache [B,nH,Smax,128] -> HF layout [B,nH,len,128]; K is stored RoPE-pair-interleaved and is de-interleaved here.
+__global__ void kv_export_kernel(const bf16* __restrict__ cache, bf16* __restrict__ out, int Smax, int len, int deinterleave) {
+  const int bh = blockIdx.y, s = blockIdx.x, c = threadIdx.x;  // 128 threads
+  const int d = deinterleave ? ((c & 1) ? 64 + (c >> 1) : (c >> 1)) : c;
+  out[((size_t)bh * len + s) * 128 + d] = cache[((size_t)bh * Smax + s) * 128 + c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int vly_create(const vly_config* cfg, vly_ctx** out) {
+  if (!cfg || !out) return fail(VLY_ERR_INVALID, "vly_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(VLY_ERR_CUDA, "vly_create: no CUDA device visible -- this library has no CPU fallback");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(VLY_ERR_CUDA, "vly_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  if (cfg->hidden_size % 128 || cfg->hidden_size / cfg->num_attention_heads != 128)
+    return fail(VLY_ERR_INVALID, "vly_create: head_dim must be 128 (hidden %d, heads %d)", cfg->hidden_size, cfg->num_attention_heads);
+  if (cfg->intermediate_size % 64) return fail(VLY_ERR_INVALID, "vly_create: intermediate_size must be a multiple of 64");
+  if (cfg->vit_hidden != 1024 || cfg->vit_hidden / cfg->vit_heads != 64 || cfg->vit_mlp % 256)
+    return fail(VLY_ERR_INVALID, "vly_create: vision tower must be ViT-L width (1024, head_dim 64); the reference hard-codes 1024 (valley_model.py:192)");
+  vly_ctx* c = new vly_ctx();
+  c->cfg = *cfg;
+  c->num_sms = prop.multiProcessorCount;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+    delete c;
+    return fail(VLY_ERR_CUDA, "vly_create: cuTensorMapEncodeTiled entry point not found");
+  }
+  c->encode = (PFN_encodeTiled)fn;
+  if (cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return fail(VLY_ERR_CUDA, "vly_create: cudaStreamCreate failed");
+  }
+  *out = c;
+  return VLY_OK;
+}
+
+extern "C" void vly_destroy(vly_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  for (auto& kvp : c->staged) cudaFree(kvp.second.dev);
+  for (void* p : c->owned) cudaFree(p);
+  Buf* bufs[] = {&c->w_col, &c->w_patch, &c->w_qkv, &c->w_ctx, &c->w_h, &c->w_stats, &c->w_pool, &c->w_x, &c->w_q, &c->w_attn, &c->w_hb, &c->w_pstats};
+  for (Buf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  delete c;
+}
+
+extern "C" int vly_num_sms(vly_ctx* c, int* out) {
+  if (!c || !out) return fail(VLY_ERR_INVALID, "null");
+  *out = c->num_sms;
+  return VLY_OK;
+}
+extern "C" int vly_kernel_launch_count(vly_ctx* c, int64_t* out) {
+  if (!c || !out) return fail(VLY_ERR_INVALID, "null");
+  *out = c->launches;
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+static bool ends_with(const std::string& s, const char* suf) {
+  const size_t n = strlen(suf);
+  return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+extern "C" int vly_load_weight(vly_ctx* c, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int ndim) {
+  if (!c || !name || !dev_ptr || !shape || ndim < 1 || ndim > 4) return fail(VLY_ERR_INVALID, "vly_load_weight: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->finalized) return fail(VLY_ERR_STATE, "vly_load_weight(%s): weights already finalised", name);
+  CK(cudaSetDevice(c->cfg.device));
+  Staged s;
+  s.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    s.shape.push_back(shape[i]);
+    s.numel *= shape[i];
+  }
+  const std::string nm(name);
+  s.is_f32 = (ndim == 1) || ends_with(nm, "position_embedding.weight");
+  auto it = c->staged.find(nm);
+  if (it != c->staged.end()) {
+    cudaFree(it->second.dev);
+    c->staged.erase(it);
+  }
+  CK(cudaMalloc(&s.dev, (size_t)s.numel * (s.is_f32 ? 4 : 2)));
+  const int blocks = (int)std::min<long long>((s.numel + 255) / 256, 4096);
+  if (s.is_f32) {
+    if (dtype == VLY_F32) convert_to_f32_bf16rounded_kernel<float><<<blocks, 256>>>((const float*)dev_ptr, (float*)s.dev, s.numel);
+    else if (dtype == VLY_BF16) convert_to_f32_bf16rounded_kernel<bf16><<<blocks, 256>>>((const bf16*)dev_ptr, (float*)s.dev, s.numel);
+    else if (dtype == VLY_F16) convert_to_f32_bf16rounded_kernel<__half><<<blocks, 256>>>((const __half*)dev_ptr, (float*)s.dev, s.numel);
+    else return fail(VLY_ERR_INVALID, "vly_load_weight(%s): unknown dtype %d", name, dtype);
+  } else {
+    if (dtype == VLY_F32) convert_to_bf16_kernel<float><<<blocks, 256>>>((const float*)dev_ptr, (bf16*)s.dev, s.numel);
+    else if (dtype == VLY_BF16) CK(cudaMemcpyAsync(s.dev, dev_ptr, (size_t)s.numel * 2, cudaMemcpyDeviceToDevice, 0));
+    else if (dtype == VLY_F16) convert_to_bf16_kernel<__half><<<blocks, 256>>>((const __half*)dev_ptr, (bf16*)s.dev, s.numel);
+    else return fail(VLY_ERR_INVALID, "vly_load_weight(%s): unknown dtype %d", name, dtype);
+  }
+  CKL();
+  CK(cudaStreamSynchronize(0));  // the caller may free its tensor right after we return
+  c->staged[nm] = s;
+  return VLY_OK;
+}
+
+template <typename T>
+static int dalloc(vly_ctx* c, T** p, size_t n) {
+  CK(cudaMalloc((void**)p, n * sizeof(T)));
+  c->owned.push_back(*p);
+  return VLY_OK;
+}
+
+static int get_staged(vly_ctx* c, const std::string& name, bool f32, int64_t numel, void** out) {
+  auto it = c->staged.find(name);
+  if (it == c->staged.end()) return fail(VLY_ERR_STATE, "vly_finalize_weights: missing tensor '%s'", name.c_str());
+  if (it->second.is_f32 != f32 || it->second.numel != numel)
+    return fail(VLY_ERR_INVALID, "vly_finalize_weights: tensor '%s' has %lld elements (expected %lld)", name.c_str(),
+                (long long)it->second.numel, (long long)numel);
+  *out = it->second.dev;
+  return VLY_OK;
+}
+static void drop_staged(vly_ctx* c, const std::string& name) {
+  auto it = c->staged.find(name);
+  if (it != c->staged.end()) {
+    cudaFree(it->second.dev);
+    c->staged.erase(it);
+  }
+}
+
+extern "C" int vly_finalize_weights(vly_ctx* c) {
+  if (!c) return fail(VLY_ERR_INVALID, "null ctx");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->finalized) return VLY_OK;
+  CK(cudaSetDevice(c->cfg.device));
+  const vly_config& g = c->cfg;
+  const std::string vp = "model.vision_tower.vision_model.";
+  c->has_vit = c->staged.count(vp + "embeddings.patch_embedding.weight") > 0;
+  c->has_llm = c->staged.count("model.embed_tokens.weight") > 0;
+  if (!c->has_vit && !c->has_llm) return fail(VLY_ERR_STATE, "vly_finalize_weights: no weights loaded");
+
+  if (c->has_vit) {
+    const int D = g.vit_hidden, M = g.vit_mlp, P = g.vit_patch, KK = 3 * P * P;
+    c->kpad = ((KK + 63) / 64) * 64;
+    const int tokens = (g.vit_image / P) * (g.vit_image / P) + 1;
+    void *pw, *cls, *pos, *pg, *pb;
+    TRY(get_staged(c, vp + "embeddings.patch_embedding.weight", false, (int64_t)D * KK, &pw));
+    TRY(get_staged(c, vp + "embeddings.class_embedding", true, D, &cls));
+    TRY(get_staged(c, vp + "embeddings.position_embedding.weight", true, (int64_t)tokens * D, &pos));
+    TRY(get_staged(c, vp + "pre_layrnorm.weight", true, D, &pg));
+    TRY(get_staged(c, vp + "pre_layrnorm.bias", true, D, &pb));
+    TRY(dalloc(c, &c->patch_w, (size_t)D * c->kpad));
+    pack_rows_kernel<<<D, 256>>>((bf16*)pw, KK, nullptr, nullptr, nullptr, c->patch_w, c->kpad, 0, 0, nullptr, nullptr);
+    CKL();
+    TRY(dalloc(c, &c->cls, D));
+    TRY(dalloc(c, &c->pos, (size_t)tokens * D));
+    TRY(dalloc(c, &c->pre_g, D));
+    TRY(dalloc(c, &c->pre_b, D));
+    CK(cudaMemcpy(c->cls, cls, D * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(c->pos, pos, (size_t)tokens * D * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(c->pre_g, pg, D * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(c->pre_b, pb, D * 4, cudaMemcpyDeviceToDevice));
+    drop_staged(c, vp + "embeddings.patch_embedding.weight");
+    c->vit.resize(g.vit_layers);
+    for (int l = 0; l < g.vit_layers; ++l) {
+      const std::string q = vp + "encoder.layers." + std::to_string(l) + ".";
+      VitLayerW& w = c->vit[l];
+      void *g1, *b1n, *g2, *b2n;
+      TRY(get_staged(c, q + "layer_norm1.weight", true, D, &g1));
+      TRY(get_staged(c, q + "layer_norm1.bias", true, D, &b1n));
+      TRY(get_staged(c, q + "layer_norm2.weight", true, D, &g2));
+      TRY(get_staged(c, q + "layer_norm2.bias", true, D, &b2n));
+      TRY(dalloc(c, &w.wqkv, (size_t)3 * D * D));
+      TRY(dalloc(c, &w.qkv_cs, 3 * D));
+      TRY(dalloc(c, &w.qkv_b, 3 * D));
+      const char* nm[3] = {"q_proj", "k_proj", "v_proj"};
+      for (int i = 0; i < 3; ++i) {
+        void *ww, *bb;
+        TRY(get_staged(c, q + "self_attn." + nm[i] + ".weight", false, (int64_t)D * D, &ww));
+        TRY(get_staged(c, q + "self_attn." + nm[i] + ".bias", true, D, &bb));
+        pack_rows_kernel<<<D, 256>>>((bf16*)ww, D, (float*)g1, (float*)b1n, (float*)bb, w.wqkv, D, 0, i * D, w.qkv_cs, w.qkv_b);
+        CKL();
+        CK(cudaDeviceSynchronize());
+        drop_staged(c, q + "self_attn." + nm[i] + ".weight");
+      }
+      void *wo, *bo, *w1, *b1, *w2, *b2;
+      TRY(get_staged(c, q + "self_attn.out_proj.weight", false, (int64_t)D * D, &wo));
+      TRY(get_staged(c, q + "self_attn.out_proj.bias", true, D, &bo));
+      TRY(get_staged(c, q + "mlp.fc1.weight", false, (int64_t)M * D, &w1));
+      TRY(get_staged(c, q + "mlp.fc1.bias", true, M, &b1));
+      TRY(get_staged(c, q + "mlp.fc2.weight", false, (int64_t)D * M, &w2));
+      TRY(get_staged(c, q + "mlp.fc2.bias", true, D, &b2));
+      TRY(dalloc(c, &w.wo, (size_t)D * D));
+      TRY(dalloc(c, &w.bo, D));
+      TRY(dalloc(c, &w.w1, (size_t)M * D));
+      TRY(dalloc(c, &w.c1, M));
+      TRY(dalloc(c, &w.b1, M));
+      TRY(dalloc(c, &w.w2, (size_t)D * M));
+      TRY(dalloc(c, &w.b2, D));
+      CK(cudaMemcpy(w.wo, wo, (size_t)D * D * 2, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(w.bo, bo, D * 4, cudaMemcpyDeviceToDevice));
+      pack_rows_kernel<<<M, 256>>>((bf16*)w1, D, (float*)g2, (float*)b2n, (float*)b1, w.w1, D, 0, 0, w.c1, w.b1);
+      CKL();
+      CK(cudaMemcpy(w.w2, w2, (size_t)D * M * 2, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(w.b2, b2, D * 4, cudaMemcpyDeviceToDevice));
+      CK(cudaDeviceSynchronize());
+      drop_staged(c, q + "self_attn.out_proj.weight");
+      drop_staged(c, q + "mlp.fc1.weight");
+      drop_staged(c, q + "mlp.fc2.weight");
+    }
+    if (c->staged.count("model.mm_projector.weight")) {
+      void *pjw, *pjb;
+      TRY(get_staged(c, "model.mm_projector.weight", false, (int64_t)g.hidden_size * D, &pjw));
+      TRY(get_staged(c, "model.mm_projector.bias", true, g.hidden_size, &pjb));
+      TRY(dalloc(c, &c->proj_w, (size_t)g.hidden_size * D));
+      TRY(dalloc(c, &c->proj_b, g.hidden_size));
+      CK(cudaMemcpy(c->proj_w, pjw, (size_t)g.hidden_size * D * 2, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(c->proj_b, pjb, g.hidden_size * 4, cudaMemcpyDeviceToDevice));
+      drop_staged(c, "model.mm_projector.weight");
+    }
+  }
+
+  if (c->has_llm) {
+    const int H = g.hidden_size, I = g.intermediate_size, V = g.vocab_size, L = g.num_hidden_layers;
+    void* emb;
+    TRY(get_staged(c, "model.embed_tokens.weight", false, (int64_t)V * H, &emb));
+    TRY(dalloc(c, &c->embed, (size_t)V * H));
+    CK(cudaMemcpy(c->embed, emb, (size_t)V * H * 2, cudaMemcpyDeviceToDevice));
+    drop_staged(c, "model.embed_tokens.weight");
+    c->layers.resize(L);
+    for (int l = 0; l < L; ++l) {
+      const std::string q = "model.layers." + std::to_string(l) + ".";
+      LlamaLayerW& w = c->layers[l];
+      void *g1, *g2;
+      TRY(get_staged(c, q + "input_layernorm.weight", true, H, &g1));
+      TRY(get_staged(c, q + "post_attention_layernorm.weight", true, H, &g2));
+      TRY(dalloc(c, &w.wqkv, (size_t)3 * H * H));
+      const char* nm[3] = {"q_proj", "k_proj", "v_proj"};
+      for (int i = 0; i < 3; ++i) {
+        void* ww;
+        TRY(get_staged(c, q + "self_attn." + nm[i] + ".weight", false, (int64_t)H * H, &ww));
+        pack_rows_kernel<<<H, 256>>>((bf16*)ww, H, (float*)g1, nullptr, nullptr, w.wqkv, H, i < 2 ? 1 : 0, i * H, nullptr, nullptr);
+        CKL();
+        CK(cudaDeviceSynchronize());
+        drop_staged(c, q + "self_attn." + nm[i] + ".weight");
+      }
+      void *wo, *wg, *wu, *wd;
+      TRY(get_staged(c, q + "self_attn.o_proj.weight", false, (int64_t)H * H, &wo));
+      TRY(get_staged(c, q + "mlp.gate_proj.weight", false, (int64_t)I * H, &wg));
+      TRY(get_staged(c, q + "mlp.up_proj.weight", false, (int64_t)I * H, &wu));
+      TRY(get_staged(c, q + "mlp.down_proj.weight", false, (int64_t)H * I, &wd));
+      TRY(dalloc(c, &w.wo, (size_t)H * H));
+      TRY(dalloc(c, &w.wgu, (size_t)2 * I * H));
+      TRY(dalloc(c, &w.wdown, (size_t)H * I));
+      CK(cudaMemcpy(w.wo, wo, (size_t)H * H * 2, cudaMemcpyDeviceToDevice));
+      pack_rows_kernel<<<I, 256>>>((bf16*)wg, H, (float*)g2, nullptr, nullptr, w.wgu, H, 2, 0, nullptr, nullptr);
+      pack_rows_kernel<<<I, 256>>>((bf16*)wu, H, (float*)g2, nullptr, nullptr, w.wgu, H, 2, 1, nullptr, nullptr);
+      CKL();
+      CK(cudaMemcpy(w.wdown, wd, (size_t)H * I * 2, cudaMemcpyDeviceToDevice));
+      CK(cudaDeviceSynchronize());
+      drop_staged(c, q + "self_attn.o_proj.weight");
+      drop_staged(c, q + "mlp.gate_proj.weight");
+      drop_staged(c, q + "mlp.up_proj.weight");
+      drop_staged(c, q + "mlp.down_proj.weight");
+    }
+    void *nf, *lm;
+    TRY(get_staged(c, "model.norm.weight", true, H, &nf));
+    TRY(get_staged(c, "lm_head.weight", false, (int64_t)V * H, &lm));
+    TRY(dalloc(c, &c->lm_head, (size_t)V * H));
+    pack_rows_kernel<<<V, 256>>>((bf16*)lm, H, (float*)nf, nullptr, nullptr, c->lm_head, H, 0, 0, nullptr, nullptr);
+    CKL();
+    CK(cudaDeviceSynchronize());
+    drop_staged(c, "lm_head.weight");
+    TRY(dalloc(c, &c->rope, (size_t)g.max_position_embeddings * 64));
+    rope_table_kernel<<<cdiv((long long)g.max_position_embeddings * 64, 256), 256>>>(c->rope, g.max_position_embeddings, g.rope_theta, 128);
+    CKL();
+  }
+  CK(cudaDeviceSynchronize());
+  for (auto& kvp : c->staged) cudaFree(kvp.second.dev);
+  c->staged.clear();
+  c->finalized = true;
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT encode
+// ------------------------------------------------------------------------------------------------
+static int launch_vit_attention(vly_ctx* c, const bf16* qkv, int F, bf16* out, cudaStream_t st) {
+  const vly_config& g = c->cfg;
+  const int D = g.vit_hidden, tokens = (g.vit_image / g.vit_patch) * (g.vit_image / g.vit_patch) + 1;
+  if (tokens != 257) return fail(VLY_ERR_INVALID, "vit attention kernel is specialised for 257 tokens (got %d)", tokens);
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VitAttnCfg::SMEM_BYTES));
+    attr = true;
+  }
+  CUtensorMap tq, tkv;
+  TRY(make_tmap_2d(c, &tq, qkv, 3 * D, (uint64_t)F * tokens, (uint64_t)3 * D * 2, 64, 128));
+  TRY(make_tmap_2d(c, &tkv, qkv, 3 * D, (uint64_t)F * tokens, (uint64_t)3 * D * 2, 64, 136));
+  VitAttnParams p;
+  p.F = F;
+  p.tokens = tokens;
+  p.heads = g.vit_heads;
+  p.D = D;
+  p.ctx = out;
+  p.scale_log2e = 0.125f * 1.4426950408889634f;
+  const int items = F * g.vit_heads;
+  const int grid = items < c->num_sms ? items : c->num_sms;
+  vit_attention_kernel<<<grid, VitAttnCfg::THREADS, VitAttnCfg::SMEM_BYTES, st>>>(tq, tkv, p);
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+
+static int vit_layers_needed(const vly_config& g, int select_layer, int* out) {
+  const int idx = select_layer >= 0 ? select_layer : g.vit_layers + 1 + select_layer;
+  if (idx < 0 || idx > g.vit_layers) return fail(VLY_ERR_INVALID, "select_layer %d out of range for %d layers", select_layer, g.vit_layers);
+  *out = idx;
+  return VLY_OK;
+}
+
+extern "C" int vly_vit_encode(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int select_layer, void* out_dev, void* stream) {
+  if (!c || !pixels || !out_dev || F <= 0) return fail(VLY_ERR_INVALID, "vly_vit_encode: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->finalized || !c->has_vit) return fail(VLY_ERR_STATE, "vly_vit_encode: vision weights not loaded/finalised");
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const vly_config& g = c->cfg;
+  const int D = g.vit_hidden, MLP = g.vit_mlp, P = g.vit_patch, IMG = g.vit_image;
+  const int NP = (IMG / P) * (IMG / P), tokens = NP + 1;
+  int n_layers;
+  TRY(vit_layers_needed(g, select_layer, &n_layers));
+  const int CH = 256;  // frames per chunk: bounds the workspace (qkv 405 MB, mlp 540 MB) and keeps tiles plentiful
+  const int fc_max = F < CH ? F : CH;
+  const size_t Mmax = (size_t)fc_max * tokens;
+  TRY(ensure(c->w_col, (size_t)fc_max * NP * c->kpad * 2));
+  TRY(ensure(c->w_patch, (size_t)fc_max * NP * D * 2));
+  TRY(ensure(c->w_qkv, Mmax * 3 * D * 2));
+  TRY(ensure(c->w_ctx, Mmax * D * 2));
+  TRY(ensure(c->w_h, Mmax * MLP * 2));
+  const int nt = cdiv(D, pick_bn(D));
+  TRY(ensure(c->w_stats, Mmax * nt * sizeof(float2)));
+  const size_t px_elem = pixel_dtype == VLY_F32 ? 4 : 2;
+  for (int f0 = 0; f0 < F; f0 += CH) {
+    const int fc = (F - f0) < CH ? (F - f0) : CH;
+    const int M = fc * tokens;
+    const char* px = (const char*)pixels + (size_t)f0 * 3 * IMG * IMG * px_elem;
+    bf16* x = (bf16*)out_dev + (size_t)f0 * tokens * D;
+    bf16* col = (bf16*)c->w_col.p;
+    const int blocks = 148 * 8;
+    if (pixel_dtype == VLY_F32) im2col_kernel<float><<<blocks, 256, 0, st>>>((const float*)px, col, fc, IMG, P, c->kpad);
+    else if (pixel_dtype == VLY_BF16) im2col_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)px, col, fc, IMG, P, c->kpad);
+    else if (pixel_dtype == VLY_F16) im2col_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)px, col, fc, IMG, P, c->kpad);
+    else return fail(VLY_ERR_INVALID, "vly_vit_encode: unknown pixel dtype %d", pixel_dtype);
+    c->launches++;
+    CKL();
+    {  // patch embedding GEMM (conv2d stride=kernel=14, no bias)
+      GemmParams p = {};
+      p.M = fc * NP; p.N = D; p.K = c->kpad;
+      p.out = c->w_patch.p; p.ldo = D;
+      TRY(launch_gemm<EPI_BIAS>(c, pick_bn(D), col, c->kpad, c->patch_w, c->kpad, p, st));
+    }
+    float2* stats = (float2*)c->w_stats.p;
+    vit_embed_ln_kernel<<<M, 128, 0, st>>>((bf16*)c->w_patch.p, c->cls, c->pos, c->pre_g, c->pre_b, x, stats, nt, tokens, D, g.vit_eps);
+    c->launches++;
+    CKL();
+    for (int l = 0; l < n_layers; ++l) {
+      const VitLayerW& w = c->vit[l];
+      {  // LN1 -> q,k,v
+        GemmParams p = {};
+        p.M = M; p.N = 3 * D; p.K = D;
+        p.out = c->w_qkv.p; p.ldo = 3 * D;
+        p.bias = w.qkv_b; p.colsum = w.qkv_cs;
+        p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / D; p.eps = g.vit_eps;
+        TRY(launch_gemm<EPI_LN_BIAS>(c, pick_bn(3 * D), x, D, w.wqkv, D, p, st));
+      }
+      TRY(launch_vit_attention(c, (bf16*)c->w_qkv.p, fc, (bf16*)c->w_ctx.p, st));
+      {  // out_proj + residual
+        GemmParams p = {};
+        p.M = M; p.N = D; p.K = D;
+        p.out = x; p.ldo = D; p.bias = w.bo; p.residual = x; p.ldr = D; p.stats_out = stats;
+        TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, pick_bn(D), (bf16*)c->w_ctx.p, D, w.wo, D, p, st));
+      }
+      {  // LN2 -> fc1 -> quick_gelu
+        GemmParams p = {};
+        p.M = M; p.N = MLP; p.K = D;
+        p.out = c->w_h.p; p.ldo = MLP; p.bias = w.b1; p.colsum = w.c1;
+        p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / D; p.eps = g.vit_eps;
+        TRY(launch_gemm<EPI_LN_BIAS_GELU>(c, pick_bn(MLP), x, D, w.w1, D, p, st));
+      }
+      {  // fc2 + residual
+        GemmParams p = {};
+        p.M = M; p.N = D; p.K = MLP;
+        p.out = x; p.ldo = D; p.bias = w.b2; p.residual = x; p.ldr = D; p.stats_out = stats;
+        TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, pick_bn(D), (bf16*)c->w_h.p, MLP, w.w2, MLP, p, st));
+      }
+    }
+  }
+  return VLY_OK;
+}
+
+extern "C" int vly_project(vly_ctx* c, const void* feats, int64_t rows, void* out, void* stream) {
+  if (!c || !feats || !out || rows <= 0) return fail(VLY_ERR_INVALID, "vly_project: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->finalized || !c->proj_w) return fail(VLY_ERR_STATE, "vly_project: mm_projector not loaded");
+  CK(cudaSetDevice(c->cfg.device));
+  GemmParams p = {};
+  p.M = (int)rows; p.N = c->cfg.hidden_size; p.K = c->cfg.vit_hidden;
+  p.out = out; p.ldo = c->cfg.hidden_size; p.bias = c->proj_b;
+  return launch_gemm<EPI_BIAS>(c, pick_bn(p.N), (const bf16*)feats, p.K, c->proj_w, p.K, p, (cudaStream_t)stream);
+}
+
+extern "C" int vly_pool_project(vly_ctx* c, const void* feats, int n_videos, int T, void* vis_rows, void* stream) {
+  if (!c || !feats || !vis_rows || n_videos <= 0 || T <= 0) return fail(VLY_ERR_INVALID, "vly_pool_project: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->finalized || !c->proj_w) return fail(VLY_ERR_STATE, "vly_pool_project: mm_projector not loaded");
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const vly_config& g = c->cfg;
+  const int D = g.vit_hidden, tokens = (g.vit_image / g.vit_patch) * (g.vit_image / g.vit_patch) + 1;
+  const int rows = tokens - 1 + T;
+  TRY(ensure(c->w_pool, (size_t)n_videos * rows * D * 2));
+  temporal_pool_kernel<<<148 * 4, 256, 0, st>>>((const bf16*)feats, (bf16*)c->w_pool.p, n_videos, T, tokens, D);
+  c->launches++;
+  CKL();
+  GemmParams p = {};
+  p.M = n_videos * rows; p.N = g.hidden_size; p.K = D;
+  p.out = vis_rows; p.ldo = g.hidden_size; p.bias = c->proj_b;
+  return launch_gemm<EPI_BIAS>(c, pick_bn(p.N), (bf16*)c->w_pool.p, D, c->proj_w, D, p, st);
+}
+
+extern "C" int vly_embed_splice(vly_ctx* c, const int64_t* ids, const int32_t* src_map, const int32_t* img_idx, const void* vis_rows,
+                                int rows_per_img, int B, int S, void* out, void* stream) {
+  if (!c || !ids || !out || B <= 0 || S <= 0) return fail(VLY_ERR_INVALID, "vly_embed_splice: bad argument");
+  if (src_map && (!img_idx || !vis_rows)) return fail(VLY_ERR_INVALID, "vly_embed_splice: src_map given without img_idx / vis_rows");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->finalized || !c->has_llm) return fail(VLY_ERR_STATE, "vly_embed_splice: LLM weights not loaded");
+  CK(cudaSetDevice(c->cfg.device));
+  embed_splice_kernel<<<B * S, 128, 0, (cudaStream_t)stream>>>((const long long*)ids, src_map, img_idx, c->embed, (const bf16*)vis_rows,
+                                                               rows_per_img, (bf16*)out, nullptr, 0, S, c->cfg.hidden_size, c->cfg.vocab_size);
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KV cache
+// ------------------------------------------------------------------------------------------------
+extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
+  if (!c || !out || batch <= 0 || max_seq <= 0) return fail(VLY_ERR_INVALID, "vly_kv_create: bad argument");
+  if (!c->finalized || !c->has_llm) return fail(VLY_ERR_STATE, "vly_kv_create: LLM weights not finalised");
+  if (max_seq > c->cfg.max_position_embeddings) return fail(VLY_ERR_INVALID, "vly_kv_create: max_seq %d > max_position_embeddings %d", max_seq, c->cfg.max_position_embeddings);
+  CK(cudaSetDevice(c->cfg.device));
+  const vly_config& g = c->cfg;
+  vly_kv* kv = new vly_kv();
+  kv->ctx = c;
+  kv->B = batch;
+  kv->Smax = (max_seq + 127) / 128 * 128;   // whole 128-key TMA tiles
+  const int H = g.hidden_size, nH = g.num_attention_heads, I = g.intermediate_size, V = g.vocab_size, L = g.num_hidden_layers;
+  const size_t cache_elems = (size_t)L * kv->layer_stride();
+  CK(cudaMalloc((void**)&kv->cache, cache_elems * 2));
+  CK(cudaMemset(kv->cache, 0, cache_elems * 2));   // padded keys must be finite: P(=0) * V(pad) must stay 0
+  // split-KV factor: enough CTAs to cover the GPU about twice
+  int ns = (2 * c->num_sms + batch * nH - 1) / (batch * nH);
+  kv->nsplit = ns < 1 ? 1 : (ns > 16 ? 16 : ns);
+  kv->gemv_grid = 2 * c->num_sms;
+  CK(cudaMalloc((void**)&kv->d_len, 8));
+  kv->d_step = kv->d_len + 1;
+  CK(cudaMemset(kv->d_len, 0, 8));
+  CK(cudaMalloc((void**)&kv->x, (size_t)batch * H * 2));
+  CK(cudaMalloc((void**)&kv->q, (size_t)batch * H * 2));
+  CK(cudaMalloc((void**)&kv->attn, (size_t)batch * H * 2));
+  CK(cudaMalloc((void**)&kv->hb, (size_t)batch * I * 2));
+  CK(cudaMalloc((void**)&kv->part_o, (size_t)batch * nH * kv->nsplit * 128 * 4));
+  CK(cudaMalloc((void**)&kv->part_ml, (size_t)batch * nH * kv->nsplit * sizeof(float2)));
+  CK(cudaMalloc((void**)&kv->counters, ((size_t)batch * nH + 1) * 4));
+  CK(cudaMemset(kv->counters, 0, ((size_t)batch * nH + 1) * 4));
+  CK(cudaMalloc((void**)&kv->part_val, (size_t)batch * kv->gemv_grid * 4));
+  CK(cudaMalloc((void**)&kv->part_idx, (size_t)batch * kv->gemv_grid * 4));
+  CK(cudaMalloc((void**)&kv->logits, (size_t)batch * V * 4));
+  CK(cudaMalloc((void**)&kv->cur_tokens, (size_t)batch * 8));
+  CK(cudaMalloc((void**)&kv->gen_tokens, (size_t)batch * kv->Smax * 8));
+  *out = kv;
+  return VLY_OK;
+}
+
+extern "C" void vly_kv_destroy(vly_kv* kv) {
+  if (!kv) return;
+  cudaSetDevice(kv->ctx->cfg.device);
+  if (kv->graph) cudaGraphExecDestroy(kv->graph);
+  void* ps[] = {kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
+  for (void* p : ps)
+    if (p) cudaFree(p);
+  delete kv;
+}
+
+extern "C" int vly_kv_seq_len(vly_kv* kv, int* out) {
+  if (!kv || !out) return fail(VLY_ERR_INVALID, "null");
+  *out = kv->host_len;
+  return VLY_OK;
+}
+
+extern "C" int vly_kv_reset(vly_kv* kv, void* stream) {
+  if (!kv) return fail(VLY_ERR_INVALID, "null");
+  CK(cudaSetDevice(kv->ctx->cfg.device));
+  kv->host_len = 0;
+  CK(cudaMemsetAsync(kv->d_len, 0, 8, (cudaStream_t)stream));
+  return VLY_OK;
+}
+
+extern "C" int vly_kv_export(vly_ctx* c, vly_kv* kv, int layer, int which, void* out, void* stream) {
+  if (!c || !kv || !out || layer < 0 || layer >= c->cfg.num_hidden_layers || (which != 0 && which != 1)) return fail(VLY_ERR_INVALID, "vly_kv_export: bad argument");
+  if (kv->host_len == 0) return VLY_OK;
+  CK(cudaSetDevice(c->cfg.device));
+  dim3 grid(kv->host_len, kv->B * c->cfg.num_attention_heads);
+  kv_export_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(which ? kv->v_layer(layer) : kv->k_layer(layer), (bf16*)out, kv->Smax, kv->host_len, which == 0);
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode-side launchers
+// ------------------------------------------------------------------------------------------------
+static size_t gemv_smem(int bmax, int K) { return (size_t)bmax * K * 2 + (size_t)(2 * 8 * 8 * bmax + 2 * 8 * bmax + 3 * bmax) * 4 + 64; }
+
+template <int MODE>
+static int launch_gemv(vly_ctx* c, GemvParams p, int grid, cudaStream_t st) {
+  const int bmax = p.B <= 1 ? 1 : (p.B <= 2 ? 2 : 4);
+  if (p.B > 4) return fail(VLY_ERR_INVALID, "gemv: batch %d > 4 per call (callers split the batch)", p.B);
+  if (p.ldx == 0) p.ldx = p.K;
+  const size_t smem = gemv_smem(bmax, p.K);
+  const int units = (p.N + 7) / 8;
+  if (grid > units) grid = units;
+#define VLY_GEMV_CASE(BM)                                                                                              \
+  {                                                                                                                    \
+    static size_t max_set = 0;                                                                                         \
+    if (smem > max_set) {                                                                                              \
+      CK(cudaFuncSetAttribute(gemv_kernel<BM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      max_set = smem;                                                                                                  \
+    }                                                                                                                  \
+    gemv_kernel<BM, MODE><<<grid, 256, smem, st>>>(p);                                                                 \
+  }
+  if (bmax == 1) VLY_GEMV_CASE(1)
+  else if (bmax == 2) VLY_GEMV_CASE(2)
+  else VLY_GEMV_CASE(4)
+#undef VLY_GEMV_CASE
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+
+// Enqueue one decode step for batch rows [b0, b0+nb) of kv (nb <= 4).  Reads kv->cur_tokens, writes kv->cur_tokens.
+static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump, cudaStream_t st) {
+  const vly_config& g = c->cfg;
+  const int H = g.hidden_size, nH = g.num_attention_heads, I = g.intermediate_size, V = g.vocab_size;
+  bf16 *x = kv->x + (size_t)b0 * H, *q = kv->q + (size_t)b0 * H, *attn = kv->attn + (size_t)b0 * H, *hb = kv->hb + (size_t)b0 * I;
+  decode_embed_kernel<<<nb, 256, 0, st>>>(kv->cur_tokens + b0, c->embed, x, H, V);
+  c->launches++;
+  CKL();
+  static bool attn_attr = false;
+  const size_t attn_smem = ((size_t)kv->Smax / kv->nsplit + 8) * 4;
+  if (!attn_attr && attn_smem > 40000) {
+    CK(cudaFuncSetAttribute(decode_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+    attn_attr = true;
+  }
+  for (int l = 0; l < g.num_hidden_layers; ++l) {
+    const LlamaLayerW& w = c->layers[l];
+    bf16* kc = kv->k_layer(l) + (size_t)b0 * nH * kv->Smax * 128;
+    bf16* vc = kv->v_layer(l) + (size_t)b0 * nH * kv->Smax * 128;
+    {
+      GemvParams p = {};
+      p.N = 3 * H; p.K = H; p.B = nb; p.W = w.wqkv; p.x = x; p.eps = g.rms_norm_eps;
+      p.out = q; p.rope = c->rope; p.seq_len = kv->d_len; p.H = H; p.nH = nH; p.Smax = kv->Smax; p.kcache = kc; p.vcache = vc;
+      TRY(launch_gemv<GEMV_QKV_ROPE>(c, p, kv->gemv_grid, st));
+    }
+    {
+      DecAttnParams p = {};
+      p.B = nb; p.nH = nH; p.H = H; p.Smax = kv->Smax; p.nsplit = kv->nsplit; p.seq_len = kv->d_len;
+      p.q = q; p.kcache = kc; p.vcache = vc;
+      p.part_o = kv->part_o + (size_t)b0 * nH * kv->nsplit * 128;
+      p.part_ml = kv->part_ml + (size_t)b0 * nH * kv->nsplit;
+      p.counters = kv->counters + (size_t)b0 * nH;
+      p.out = attn;
+      p.scale_log2e = 0.08838834764831845f * 1.4426950408889634f;
+      dim3 grid(nb * nH, kv->nsplit);
+      decode_attention_kernel<<<grid, 128, attn_smem, st>>>(p);
+      c->launches++;
+      CKL();
+    }
+    {
+      GemvParams p = {};
+      p.N = H; p.K = H; p.B = nb; p.W = w.wo; p.x = attn; p.out = x; p.res = x;
+      TRY(launch_gemv<GEMV_RESIDUAL>(c, p, kv->gemv_grid, st));
+    }
+    {
+      GemvParams p = {};
+      p.N = 2 * I; p.K = H; p.B = nb; p.W = w.wgu; p.x = x; p.eps = g.rms_norm_eps; p.out = hb;
+      TRY(launch_gemv<GEMV_SWIGLU>(c, p, kv->gemv_grid, st));
+    }
+    {
+      GemvParams p = {};
+      p.N = H; p.K = I; p.B = nb; p.W = w.wdown; p.x = hb; p.out = x; p.res = x;
+      TRY(launch_gemv<GEMV_RESIDUAL>(c, p, kv->gemv_grid, st));
+    }
+  }
+  {
+    GemvParams p = {};
+    p.N = V; p.K = H; p.B = nb; p.W = c->lm_head; p.x = x; p.eps = g.rms_norm_eps;
+    p.logits = kv->logits + (size_t)b0 * V;
+    p.part_val = kv->part_val + (size_t)b0 * kv->gemv_grid;
+    p.part_idx = kv->part_idx + (size_t)b0 * kv->gemv_grid;
+    p.counter = kv->counters + (size_t)kv->B * nH;
+    p.next_tokens = kv->cur_tokens + b0;
+    p.out_tokens = kv->gen_tokens + (size_t)b0 * kv->Smax;
+    p.out_stride = kv->Smax;
+    p.step = kv->d_step;
+    p.seq_len_rw = kv->d_len;
+    p.bump = bump ? 1 : 0;   // only the last batch group of a step advances the step / length counters
+    TRY(launch_gemv<GEMV_LOGITS>(c, p, kv->gemv_grid, st));
+  }
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prefill
+// ------------------------------------------------------------------------------------------------
+static int launch_prefill_attention(vly_ctx* c, vly_kv* kv, const bf16* qbuf, int B, int S, int past, int layer, bf16* out, cudaStream_t st) {
+  const vly_config& g = c->cfg;
+  const int H = g.hidden_size, nH = g.num_attention_heads;
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(llama_prefill_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PrefillAttnCfg::SMEM_BYTES));
+    attr = true;
+  }
+  CUtensorMap tq, tk, tv;
+  TRY(make_tmap_2d(c, &tq, qbuf, H, (uint64_t)B * S, (uint64_t)H * 2, 64, 128));
+  TRY(make_tmap_3d(c, &tk, kv->k_layer(layer), 128, kv->Smax, (uint64_t)B * nH, 256, (uint64_t)kv->Smax * 256, 64, 128));
+  TRY(make_tmap_3d(c, &tv, kv->v_layer(layer), 128, kv->Smax, (uint64_t)B * nH, 256, (uint64_t)kv->Smax * 256, 64, 128));
+  PrefillAttnParams p;
+  p.B = B; p.S = S; p.past = past; p.nH = nH; p.H = H; p.Smax = kv->Smax; p.ctx = out;
+  p.scale_log2e = 0.08838834764831845f * 1.4426950408889634f;
+  const int n_qt = cdiv(S, 128);
+  llama_prefill_attention_kernel<<<B * nH * n_qt, PrefillAttnCfg::THREADS, PrefillAttnCfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+
+extern "C" int vly_llama_prefill(vly_ctx* c, vly_kv* kv, const void* inputs_embeds, int B, int S, int logits_mode, void* logits_dev,
+                                 int64_t* next_tokens_dev, void* stream) {
+  if (!c || !kv || !inputs_embeds || B <= 0 || S <= 0) return fail(VLY_ERR_INVALID, "vly_llama_prefill: bad argument");
+  if (kv->ctx != c || B != kv->B) return fail(VLY_ERR_INVALID, "vly_llama_prefill: batch %d does not match the kv cache (%d)", B, kv->B);
+  if (logits_mode < 0 || logits_mode > 2 || (logits_mode && !logits_dev)) return fail(VLY_ERR_INVALID, "vly_llama_prefill: bad logits mode");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->finalized || !c->has_llm) return fail(VLY_ERR_STATE, "vly_llama_prefill: LLM weights not finalised");
+  const int past = kv->host_len;
+  if (past + S > kv->Smax) return fail(VLY_ERR_INVALID, "vly_llama_prefill: %d cached + %d new tokens exceed the cache capacity %d", past, S, kv->Smax);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const vly_config& g = c->cfg;
+  const int H = g.hidden_size, nH = g.num_attention_heads, I = g.intermediate_size, V = g.vocab_size;
+  const int M = B * S;
+  const int bn_h = pick_bn(H), nt = cdiv(H, bn_h);
+  TRY(ensure(c->w_x, (size_t)M * H * 2));
+  TRY(ensure(c->w_q, (size_t)M * H * 2));
+  TRY(ensure(c->w_attn, (size_t)M * H * 2));
+  TRY(ensure(c->w_hb, (size_t)M * I * 2));
+  TRY(ensure(c->w_pstats, (size_t)M * nt * sizeof(float2)));
+  bf16 *x = (bf16*)c->w_x.p, *qb = (bf16*)c->w_q.p, *attn = (bf16*)c->w_attn.p, *hb = (bf16*)c->w_hb.p;
+  float2* stats = (float2*)c->w_pstats.p;
+  copy_rows_stats_kernel<<<M, 128, 0, st>>>((const bf16*)inputs_embeds, x, stats, nt, H);
+  c->launches++;
+  CKL();
+  for (int l = 0; l < g.num_hidden_layers; ++l) {
+    const LlamaLayerW& w = c->layers[l];
+    {
+      GemmParams p = {};
+      p.M = M; p.N = 3 * H; p.K = H; p.out = qb; p.ldo = H;
+      p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / H; p.eps = g.rms_norm_eps;
+      p.rope = c->rope; p.S = S; p.past = past; p.H = H; p.nH = nH; p.Smax = kv->Smax;
+      p.kcache = kv->k_layer(l); p.vcache = kv->v_layer(l);
+      TRY(launch_gemm<EPI_RMS_QKV_ROPE>(c, pick_bn(3 * H), x, H, w.wqkv, H, p, st));
+    }
+    TRY(launch_prefill_attention(c, kv, qb, B, S, past, l, attn, st));
+    {
+      GemmParams p = {};
+      p.M = M; p.N = H; p.K = H; p.out = x; p.ldo = H; p.residual = x; p.ldr = H; p.stats_out = stats;
+      TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, bn_h, attn, H, w.wo, H, p, st));
+    }
+    {
+      GemmParams p = {};
+      p.M = M; p.N = 2 * I; p.K = H; p.out = hb; p.ldo = I;
+      p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / H; p.eps = g.rms_norm_eps;
+      TRY(launch_gemm<EPI_RMS_SWIGLU>(c, pick_bn(2 * I), x, H, w.wgu, H, p, st));
+    }
+    {
+      GemmParams p = {};
+      p.M = M; p.N = H; p.K = I; p.out = x; p.ldo = H; p.residual = x; p.ldr = H; p.stats_out = stats;
+      TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, bn_h, hb, I, w.wdown, I, p, st));
+    }
+  }
+  if (logits_mode == 2) {  // lm_head over every position (valley_model.py:304-305)
+    GemmParams p = {};
+    p.M = M; p.N = V; p.K = H; p.out = logits_dev; p.ldo = V;
+    p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / H; p.eps = g.rms_norm_eps;
+    TRY(launch_gemm<EPI_RMS_F32>(c, 256, x, H, c->lm_head, H, p, st));
+  }
+  // last position only: final RMSNorm (folded) + lm_head GEMV + greedy argmax (model_worker.py:389-391)
+  for (int b0 = 0; b0 < B; b0 += 4) {
+    const int nb = (B - b0) < 4 ? (B - b0) : 4;
+    GemvParams p = {};
+    p.N = V; p.K = H; p.B = nb; p.W = c->lm_head; p.x = x + ((size_t)b0 * S + (S - 1)) * H; p.ldx = (long long)S * H;
+    p.eps = g.rms_norm_eps;
+    p.logits = kv->logits + (size_t)b0 * V;
+    p.part_val = kv->part_val + (size_t)b0 * kv->gemv_grid;
+    p.part_idx = kv->part_idx + (size_t)b0 * kv->gemv_grid;
+    p.counter = kv->counters + (size_t)kv->B * nH;
+    p.next_tokens = kv->cur_tokens + b0;
+    p.out_tokens = nullptr;
+    p.step = kv->d_step; p.seq_len_rw = kv->d_len; p.bump = 0;
+    TRY(launch_gemv<GEMV_LOGITS>(c, p, kv->gemv_grid, st));
+  }
+  if (logits_mode == 1) CK(cudaMemcpyAsync(logits_dev, kv->logits, (size_t)B * V * 4, cudaMemcpyDeviceToDevice, st));
+  if (next_tokens_dev) CK(cudaMemcpyAsync(next_tokens_dev, kv->cur_tokens, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+  kv->host_len = past + S;
+  set_int_kernel<<<1, 1, 0, st>>>(kv->d_len, kv->host_len);
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+static int enqueue_full_step(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
+  for (int b0 = 0; b0 < kv->B; b0 += 4) {
+    const int nb = (kv->B - b0) < 4 ? (kv->B - b0) : 4;
+    TRY(enqueue_decode_step(c, kv, b0, nb, b0 + 4 >= kv->B, st));
+  }
+  return VLY_OK;
+}
+
+static int build_graph(vly_ctx* c, vly_kv* kv) {
+  if (kv->graph) return VLY_OK;
+  const int64_t before = c->launches;
+  CK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int r = enqueue_full_step(c, kv, c->cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
+  kv->graph_nodes = (int)(c->launches - before);
+  c->launches = before;
+  if (r != VLY_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return r;
+  }
+  if (e != cudaSuccess) return fail(VLY_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  const cudaError_t e2 = cudaGraphInstantiate(&kv->graph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess) return fail(VLY_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2));
+  return VLY_OK;
+}
+
+extern "C" int vly_generate_greedy(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, int n_steps, int64_t* out_tokens, void* stream) {
+  if (!c || !kv || !first_tokens || n_steps <= 0 || kv->ctx != c) return fail(VLY_ERR_INVALID, "vly_generate_greedy: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kv->host_len + n_steps > kv->Smax) return fail(VLY_ERR_INVALID, "vly_generate_greedy: %d cached + %d steps exceed the cache capacity %d", kv->host_len, n_steps, kv->Smax);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(build_graph(c, kv));
+  CK(cudaMemcpyAsync(kv->cur_tokens, first_tokens, (size_t)kv->B * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(kv->d_step, 0, 4, st));
+  for (int i = 0; i < n_steps; ++i) CK(cudaGraphLaunch(kv->graph, st));
+  c->launches += (int64_t)n_steps * kv->graph_nodes;
+  if (out_tokens)
+    CK(cudaMemcpy2DAsync(out_tokens, (size_t)n_steps * 8, kv->gen_tokens, (size_t)kv->Smax * 8, (size_t)n_steps * 8, kv->B,
+                         cudaMemcpyDeviceToDevice, st));
+  kv->host_len += n_steps;
+  return VLY_OK;
+}
+
+extern "C" int vly_llama_decode(vly_ctx* c, vly_kv* kv, const int64_t* tokens, int64_t* next_tokens, void* logits_dev, void* stream) {
+  if (!c || !kv || !tokens || kv->ctx != c) return fail(VLY_ERR_INVALID, "vly_llama_decode: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kv->host_len + 1 > kv->Smax) return fail(VLY_ERR_INVALID, "vly_llama_decode: cache full (%d)", kv->Smax);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(build_graph(c, kv));
+  CK(cudaMemcpyAsync(kv->cur_tokens, tokens, (size_t)kv->B * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(kv->d_step, 0, 4, st));
+  CK(cudaGraphLaunch(kv->graph, st));
+  c->launches += kv->graph_nodes;
+  if (next_tokens) CK(cudaMemcpyAsync(next_tokens, kv->cur_tokens, (size_t)kv->B * 8, cudaMemcpyDeviceToDevice, st));
+  if (logits_dev) CK(cudaMemcpyAsync(logits_dev, kv->logits, (size_t)kv->B * c->cfg.vocab_size * 4, cudaMemcpyDeviceToDevice, st));
+  kv->host_len += 1;
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-kernel test hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int vly_test_gemm(vly_ctx* c, const void* a, const void* w, int M, int N, int K, int epi, const float* bias, const void* residual,
+                             void* out, int block_n, void* stream) {
+  if (!c || !a || !w || !out || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (block_n != 128 && block_n != 256))
+    return fail(VLY_ERR_INVALID, "vly_test_gemm: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CK(cudaSetDevice(c->cfg.device));
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = N; p.bias = bias;
+  if (epi == EPI_BIAS) return launch_gemm<EPI_BIAS>(c, block_n, (const bf16*)a, K, (const bf16*)w, K, p, (cudaStream_t)stream);
+  if (epi == EPI_BIAS_RES_STATS) {
+    if (!residual || (N % 32)) return fail(VLY_ERR_INVALID, "vly_test_gemm: residual epilogue needs a residual and N %% 32 == 0");
+    p.residual = (const bf16*)residual; p.ldr = N;
+    return launch_gemm<EPI_BIAS_RES_STATS>(c, block_n, (const bf16*)a, K, (const bf16*)w, K, p, (cudaStream_t)stream);
+  }
+  return fail(VLY_ERR_INVALID, "vly_test_gemm: unsupported epilogue %d", epi);
+}
+
+extern "C" int vly_test_vit_attention(vly_ctx* c, const void* qkv, int F, void* out, void* stream) {
+  if (!c || !qkv || !out || F <= 0) return fail(VLY_ERR_INVALID, "vly_test_vit_attention: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CK(cudaSetDevice(c->cfg.device));
+  return launch_vit_attention(c, (const bf16*)qkv, F, (bf16*)out, (cudaStream_t)stream);
+}

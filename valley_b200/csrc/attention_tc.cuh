@@ -1,0 +1,541 @@
+// tcgen05 attention kernels.
+//
+//  vit_attention_kernel    : CLIP ViT-L/14 self-attention (HF:modeling_clip.py:261-279, :300-336):
+//                            257 tokens, 16 heads x 64, no mask.  All 257 keys of a (frame, head) fit on
+//                            chip, so S = Q K^T for a 128-row query tile lives entirely in TMEM (272 fp32
+//                            columns), softmax is a single pass, P goes to shared memory as bf16 and
+//                            O = P V accumulates in TMEM.  V is consumed as an MN-major B operand straight
+//                            from the row-major QKV buffer (no transpose pass).
+//  llama_prefill_attention : causal attention with KV cache (HF:modeling_llama.py:199-222, :251-289),
+//                            head_dim 128, two-pass flash style: pass 1 computes the row max / sum over all
+//                            key blocks, pass 2 recomputes S, writes P = exp(s - max) and accumulates
+//                            O += P V in TMEM without rescaling.  Prefill attention is ~1% of prefill FLOPs
+//                            at S~340, so the recompute is irrelevant; what matters is exactness.
+#pragma once
+#include "common.cuh"
+
+namespace vly {
+
+// Write 8 bf16 (16 B) of row `r`, columns [col, col+8) into a K-major SWIZZLE_128B operand made of
+// 64-column blocks of `rows_per_block` rows (block stride = rows_per_block * 128 B).
+VLY_DEVINL void st_sw128_row16(uint8_t* base, int rows_per_block, int r, int col, uint4 v) {
+  const int cb = col >> 6, c16 = (col & 63) >> 3;
+  uint8_t* p = base + (size_t)cb * rows_per_block * 128 + r * 128 + ((c16 ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+// ============================================================================================
+// ViT attention
+// ============================================================================================
+struct VitAttnParams {
+  int F;                    // frames
+  int tokens;               // 257
+  int heads;                // 16
+  int D;                    // 1024
+  __nv_bfloat16* ctx;       // [F*tokens, D]
+  float scale_log2e;        // head_dim^-0.5 * log2(e)
+};
+
+struct VitAttnCfg {
+  static constexpr int KEYS_PAD = 272;                    // 257 padded to a multiple of 16 (UMMA K step) and 8 (atom)
+  static constexpr int Q_BYTES = 128 * 128;               // 128 rows x 64 bf16
+  static constexpr int KV_BYTES = KEYS_PAD * 128;         // 272 rows x 64 bf16
+  static constexpr int P_BLOCKS = 5;                      // 272 key columns -> 5 blocks of 64
+  static constexpr int P_BYTES = P_BLOCKS * 128 * 128;
+  static constexpr int OFF_Q = 0;                         // two Q buffers
+  static constexpr int OFF_K = 2 * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int THREADS = 160;                     // warp 0: TMA + MMA issue; warps 1-4: softmax / epilogue
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int O_COL = 320;
+};
+
+// tma_q : 2D map over qkv [F*257, 3*D], box {64, 128};  tma_kv : same tensor, box {64, 136}
+__global__ void __launch_bounds__(160, 1)
+vit_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                     const VitAttnParams p) {
+  using C = VitAttnCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;   // [2]
+  uint64_t* s_full = bars + 3;
+  uint64_t* p_full = bars + 4;
+  uint64_t* o_full = bars + 5;
+  uint64_t* o_empty = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.F * p.heads;
+  const int n_qt = (p.tokens + 127) / 128;   // 3
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s256 = make_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_s16 = make_idesc_bf16(128, 16);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, /*b MN-major*/ 1);
+      uint32_t kv_ph = 0, q_ph[2] = {0, 0}, p_ph = 0, oe_ph = 0;
+      uint32_t o_ph = (n_qt - 1) & 1;  // parity of the LAST o_full phase of the first item
+      int t_global = 0;  // running tile counter (selects the Q buffer)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int f = item / p.heads, h = item % p.heads;
+        const int row0 = f * p.tokens;
+        // K and V of this (frame, head): rows row0 .. row0+271 (rows past the frame are masked / multiplied by 0)
+        mbar_expect_tx(kv_full, 2 * C::KV_BYTES);
+        tma_load_2d(smem + C::OFF_K, &tma_kv, kv_full, p.D + h * 64, row0);
+        tma_load_2d(smem + C::OFF_K + 136 * 128, &tma_kv, kv_full, p.D + h * 64, row0 + 136);
+        tma_load_2d(smem + C::OFF_V, &tma_kv, kv_full, 2 * p.D + h * 64, row0);
+        tma_load_2d(smem + C::OFF_V + 136 * 128, &tma_kv, kv_full, 2 * p.D + h * 64, row0 + 136);
+        // first Q tile
+        {
+          const int qb = t_global & 1;
+          mbar_expect_tx(&q_full[qb], C::Q_BYTES);
+          tma_load_2d(smem + C::OFF_Q + qb * C::Q_BYTES, &tma_q, &q_full[qb], h * 64, row0);
+        }
+        mbar_wait(kv_full, kv_ph);
+        kv_ph ^= 1;
+        for (int qt = 0; qt < n_qt; ++qt, ++t_global) {
+          const int qb = t_global & 1;
+          mbar_wait(&q_full[qb], q_ph[qb]);
+          q_ph[qb] ^= 1;
+          tc_fence_after();
+          // ---- S = Q K^T : K=64 -> 4 k-steps, N = 256 + 16 ----
+          const uint32_t q_addr = base_u32 + C::OFF_Q + qb * C::Q_BYTES;
+          const uint32_t k_addr = base_u32 + C::OFF_K;
+          const uint64_t dq = make_smem_desc_sw128(q_addr, 16, 1024);
+          const uint64_t dk0 = make_smem_desc_sw128(k_addr, 16, 1024);
+          const uint64_t dk1 = make_smem_desc_sw128(k_addr + 256 * 128, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc_mma_bf16(tmem_base + 0, dq + 2 * k, dk0 + 2 * k, idesc_s256, k != 0);
+            tc_mma_bf16(tmem_base + 256, dq + 2 * k, dk1 + 2 * k, idesc_s16, k != 0);
+          }
+          tc_commit(s_full);
+          // prefetch the next Q tile of this item into the other buffer (its last reader, the S-MMA of
+          // tile t-1, completed before p_full(t-1) which we already waited on)
+          if (qt + 1 < n_qt) {
+            const int nb = (t_global + 1) & 1;
+            mbar_expect_tx(&q_full[nb], C::Q_BYTES);
+            tma_load_2d(smem + C::OFF_Q + nb * C::Q_BYTES, &tma_q, &q_full[nb], h * 64, row0 + (qt + 1) * 128);
+          }
+          // ---- wait for P (bf16 in smem), previous O drained ----
+          mbar_wait(p_full, p_ph);
+          p_ph ^= 1;
+          mbar_wait(o_empty, oe_ph ^ 1);
+          oe_ph ^= 1;
+          tc_fence_after();
+          // ---- O = P V : K = 272 keys -> 17 k-steps; A = P (K-major), B = V (MN-major, N = 64) ----
+          const uint32_t p_addr = base_u32 + C::OFF_P, v_addr = base_u32 + C::OFF_V;
+#pragma unroll 1
+          for (int j = 0; j < C::KEYS_PAD / 16; ++j) {
+            const uint64_t dp = make_smem_desc_sw128(p_addr + (j >> 2) * (128 * 128) + (j & 3) * 32, 16, 1024);
+            const uint64_t dv = make_smem_desc_sw128(v_addr + j * 16 * 128, 16, 1024);
+            tc_mma_bf16(tmem_base + C::O_COL, dp, dv, idesc_pv, j != 0);
+          }
+          tc_commit(o_full);
+        }
+        // K/V smem is overwritten by the next item: all PV MMAs must have retired
+        mbar_wait(o_full, o_ph);
+        o_ph ^= (n_qt & 1);   // o_full completes n_qt phases per item; we only observe the last one
+      }
+    }
+  } else {
+    // ================= softmax + epilogue: one query row per thread =================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    uint32_t s_ph = 0, o_ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int f = item / p.heads, h = item % p.heads;
+      for (int qt = 0; qt < n_qt; ++qt) {
+        const int qrow = qt * 128 + r;
+        const bool warp_active = (qt * 128 + quad * 32) < p.tokens;  // warp-uniform
+        __syncwarp();
+        mbar_wait(s_full, s_ph);
+        s_ph ^= 1;
+        tc_fence_after();
+        float row_sum = 1.f;
+        if (warp_active) {
+          // pass 1: row max over the 257 valid keys
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + lane_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+          {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_base + lane_addr + 256, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (256 + i < p.tokens) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+          const float mb = mx * p.scale_log2e;
+          // pass 2: p = exp2(s*scale*log2e - max*scale*log2e), write bf16 P, accumulate the row sum
+          float sum = 0.f;
+          uint8_t* sP = smem + C::OFF_P;
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + lane_addr + c * 32, v);
+            tmem_ld_wait();
+            float e[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              e[i] = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb));
+              sum += e[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_sw128_row16(sP, 128, r, c * 32 + j * 8,
+                             make_uint4(pack_bf16x2(e[8 * j], e[8 * j + 1]), pack_bf16x2(e[8 * j + 2], e[8 * j + 3]),
+                                        pack_bf16x2(e[8 * j + 4], e[8 * j + 5]), pack_bf16x2(e[8 * j + 6], e[8 * j + 7])));
+          }
+          {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_base + lane_addr + 256, v);
+            tmem_ld_wait();
+            float e[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              e[i] = (256 + i < p.tokens) ? fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb)) : 0.f;
+              sum += e[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              st_sw128_row16(sP, 128, r, 256 + j * 8,
+                             make_uint4(pack_bf16x2(e[8 * j], e[8 * j + 1]), pack_bf16x2(e[8 * j + 2], e[8 * j + 3]),
+                                        pack_bf16x2(e[8 * j + 4], e[8 * j + 5]), pack_bf16x2(e[8 * j + 6], e[8 * j + 7])));
+          }
+          row_sum = sum;
+        } else {
+          // rows past the last token: P must still be finite (0) so the MMA does not produce NaN garbage
+          uint8_t* sP = smem + C::OFF_P;
+          for (int col = 0; col < C::KEYS_PAD; col += 8) st_sw128_row16(sP, 128, r, col, make_uint4(0, 0, 0, 0));
+        }
+        // generic-proxy smem writes -> visible to the tensor core (async proxy); S fully consumed
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_full);
+
+        // ---- epilogue: O / sum -> ctx ----
+        __syncwarp();
+        mbar_wait(o_full, o_ph);
+        o_ph ^= 1;
+        tc_fence_after();
+        if (warp_active) {
+          const float inv = __frcp_rn(row_sum);
+          __nv_bfloat16* dst = p.ctx + ((size_t)f * p.tokens + qrow) * p.D + h * 64;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + lane_addr + C::O_COL + c * 32, v);
+            tmem_ld_wait();
+            if (qrow < p.tokens) {
+              uint4* op = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                op[j] = make_uint4(
+                    pack_bf16x2(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv),
+                    pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv),
+                    pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv),
+                    pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv));
+            }
+          }
+        }
+        __syncwarp();
+        tc_fence_before();
+        mbar_arrive(o_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ============================================================================================
+// LLaMA prefill attention (causal, head_dim 128, KV cache [B, nH, Smax, 128], q/k in the
+// RoPE-interleaved column order written by the QKV epilogue; v and the output in natural order)
+// ============================================================================================
+struct PrefillAttnParams {
+  int B, S, past, nH, H, Smax;
+  __nv_bfloat16* ctx;   // [B*S, H]
+  float scale_log2e;    // 128^-0.5 * log2(e)
+};
+
+struct PrefillAttnCfg {
+  static constexpr int TILE_BYTES = 128 * 128;             // 128 rows x 64 bf16 (one 64-col block)
+  static constexpr int OFF_Q = 0;                          // 2 blocks
+  static constexpr int OFF_K = 2 * TILE_BYTES;             // 2 stages x 2 blocks
+  static constexpr int OFF_V = OFF_K + 4 * TILE_BYTES;     // 2 stages x 2 blocks
+  static constexpr int OFF_P = OFF_V + 4 * TILE_BYTES;     // 2 blocks
+  static constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int THREADS = 192;                      // warp 0 TMA, warp 1 MMA, warps 2-5 softmax
+  static constexpr int TMEM_COLS = 256;                    // S [0,128), O [128,256)
+};
+
+// tma_q : 2D over qbuf [B*S, H], box {64,128};  tma_k / tma_v : 3D over cache {128, Smax, B*nH}, box {64,128,1}
+__global__ void __launch_bounds__(192, 1)
+llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                               const __grid_constant__ CUtensorMap tma_v, const PrefillAttnParams p) {
+  using C = PrefillAttnCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* p_empty = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qt = (p.S + 127) / 128;
+  const int qt = blockIdx.x % n_qt;
+  const int bh = blockIdx.x / n_qt;          // b * nH + h
+  const int b = bh / p.nH, h = bh % p.nH;
+  const int kv_len = p.past + p.S;
+  const int q_hi = min(p.S, (qt + 1) * 128);                 // one past the last query row of this tile
+  const int nkv = (p.past + q_hi + 127) / 128;               // key blocks any row of the tile can see
+  const int n_iter = 2 * nkv;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * C::TILE_BYTES);
+      tma_load_2d(smem + C::OFF_Q, &tma_q, q_full, h * 128, b * p.S + qt * 128);
+      tma_load_2d(smem + C::OFF_Q + C::TILE_BYTES, &tma_q, q_full, h * 128 + 64, b * p.S + qt * 128);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int j = it % nkv, pass = it / nkv;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], (pass ? 4 : 2) * C::TILE_BYTES);
+        uint8_t* kd = smem + C::OFF_K + st * 2 * C::TILE_BYTES;
+        tma_load_3d(kd, &tma_k, &kv_full[st], 0, j * 128, bh);
+        tma_load_3d(kd + C::TILE_BYTES, &tma_k, &kv_full[st], 64, j * 128, bh);
+        if (pass) {
+          uint8_t* vd = smem + C::OFF_V + st * 2 * C::TILE_BYTES;
+          tma_load_3d(vd, &tma_v, &kv_full[st], 0, j * 128, bh);
+          tma_load_3d(vd + C::TILE_BYTES, &tma_v, &kv_full[st], 64, j * 128, bh);
+        }
+        if (++st == 2) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);
+      mbar_wait(q_full, 0);
+      int st = 0;
+      uint32_t ph = 0, se_ph = 0, pf_ph = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int j = it % nkv, pass = it / nkv;
+        mbar_wait(&kv_full[st], ph);
+        mbar_wait(s_empty, se_ph ^ 1);   // softmax finished reading the previous S
+        se_ph ^= 1;
+        tc_fence_after();
+        const uint32_t q_addr = base_u32 + C::OFF_Q;
+        const uint32_t k_addr = base_u32 + C::OFF_K + st * 2 * C::TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * C::TILE_BYTES + (kk & 3) * 32;
+          tc_mma_bf16(tmem_base + 0, make_smem_desc_sw128(q_addr + off, 16, 1024),
+                      make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s, kk != 0);
+        }
+        tc_commit(s_full);
+        if (!pass) {
+          tc_commit(&kv_empty[st]);
+        } else {
+          mbar_wait(p_full, pf_ph);
+          pf_ph ^= 1;
+          tc_fence_after();
+          const uint32_t p_addr = base_u32 + C::OFF_P;
+          const uint32_t v_addr = base_u32 + C::OFF_V + st * 2 * C::TILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            // A = P[128 rows, keys kk*16..+16): key block (kk>>2), 32 B per k-step inside the atom
+            // B = V[keys kk*16..+16, d 0..127] MN-major: 16 keys = 2 atoms of 1024 B; d chunks 16 KB apart (LBO)
+            tc_mma_bf16(tmem_base + 128,
+                        make_smem_desc_sw128(p_addr + (kk >> 2) * C::TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                        make_smem_desc_sw128(v_addr + kk * 16 * 128, C::TILE_BYTES, 1024), idesc_pv,
+                        (j | kk) != 0);
+          }
+          tc_commit(&kv_empty[st]);
+          tc_commit(p_empty);
+          if (it == n_iter - 1) tc_commit(o_full);
+        }
+        if (++st == 2) { st = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const int q_idx = qt * 128 + r;           // query index within the sequence
+    const int q_pos = p.past + q_idx;         // absolute position
+    uint32_t sf_ph = 0, pe_ph = 0;
+    float m = -INFINITY, l = 0.f;
+    // ---------------- pass 1: running max / sum ----------------
+    for (int j = 0; j < nkv; ++j) {
+      __syncwarp();
+      mbar_wait(s_full, sf_ph);
+      sf_ph ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        float s[32], cm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int key = j * 128 + c * 32 + i;
+          s[i] = (key <= q_pos && key < kv_len) ? __uint_as_float(v[i]) * p.scale_log2e : -INFINITY;
+          cm = fmaxf(cm, s[i]);
+        }
+        const float mn = fmaxf(m, cm);
+        if (mn > -INFINITY) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc += fast_exp2(s[i] - mn);
+          l = l * fast_exp2(m - mn) + acc;
+          m = mn;
+        }
+      }
+      __syncwarp();
+      tc_fence_before();
+      mbar_arrive(s_empty);
+    }
+    // ---------------- pass 2: P = exp2(s - m) -> smem, O += P V ----------------
+    uint8_t* sP = smem + C::OFF_P;
+    for (int j = 0; j < nkv; ++j) {
+      __syncwarp();
+      mbar_wait(s_full, sf_ph);
+      sf_ph ^= 1;
+      mbar_wait(p_empty, pe_ph ^ 1);   // previous PV MMAs no longer read sP
+      pe_ph ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int key = j * 128 + c * 32 + i;
+          e[i] = (key <= q_pos && key < kv_len) ? fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, -m)) : 0.f;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          st_sw128_row16(sP, 128, r, c * 32 + jj * 8,
+                         make_uint4(pack_bf16x2(e[8 * jj], e[8 * jj + 1]), pack_bf16x2(e[8 * jj + 2], e[8 * jj + 3]),
+                                    pack_bf16x2(e[8 * jj + 4], e[8 * jj + 5]), pack_bf16x2(e[8 * jj + 6], e[8 * jj + 7])));
+      }
+      __syncwarp();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      mbar_arrive(p_full);
+    }
+    // ---------------- epilogue ----------------
+    __syncwarp();
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = __frcp_rn(l);
+    __nv_bfloat16* dst = p.ctx + ((size_t)b * p.S + q_idx) * p.H + h * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + lane_addr + 128 + c * 32, v);
+      tmem_ld_wait();
+      if (q_idx < p.S) {
+        uint4* op = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          op[jj] = make_uint4(
+              pack_bf16x2(__uint_as_float(v[8 * jj]) * inv, __uint_as_float(v[8 * jj + 1]) * inv),
+              pack_bf16x2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv),
+              pack_bf16x2(__uint_as_float(v[8 * jj + 4]) * inv, __uint_as_float(v[8 * jj + 5]) * inv),
+              pack_bf16x2(__uint_as_float(v[8 * jj + 6]) * inv, __uint_as_float(v[8 * jj + 7]) * inv));
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+}  // namespace vly

@@ -1,0 +1,339 @@
+// Persistent, warp-specialised tcgen05 GEMM:  D[M,N] = A[M,K] * B[N,K]^T   (bf16 in, fp32 accumulate in TMEM)
+//
+//   warp 0      : TMA producer  (A tile 128x64, B tile BNx64 per stage, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16), tcgen05.commit
+//   warps 2..5  : epilogue -- tcgen05.ld the accumulator (one TMEM lane == one output row per thread),
+//                 apply the fused epilogue, store.  Two accumulator stages in TMEM so the epilogue
+//                 of tile i overlaps the main loop of tile i+1.
+//
+// Both operands are K-major, i.e. A is a row-major activation matrix and B is an nn.Linear weight
+// [out_features, in_features] exactly as HuggingFace stores it.
+//
+// Fused epilogues (what the reference runs as separate ATen kernels):
+//   LayerNorm / RMSNorm *prologue*:  LN(x) W^T = rstd * (x W'^T - mean * colsum(W')) + (b + W beta),
+//     W' = W * gamma folded at load time, so the GEMM runs on the raw residual stream and the row
+//     statistics (mean, rstd) are applied here.  The statistics arrive as per-row partial (sum, sumsq)
+//     pairs written by the epilogue of the GEMM that produced x (deterministic, no atomics).
+//   bias, quick_gelu, residual add, SwiGLU (gate/up rows interleaved), RoPE + KV-cache append.
+#pragma once
+#include "common.cuh"
+
+namespace vly {
+
+enum EpiMode : int {
+  EPI_BIAS = 0,           // out = acc (+ bias)                                    -> bf16
+  EPI_LN_BIAS = 1,        // out = rstd*(acc - mean*colsum) + bias                 -> bf16   (ViT QKV)
+  EPI_LN_BIAS_GELU = 2,   // quick_gelu(rstd*(acc - mean*colsum) + bias)           -> bf16   (ViT fc1)
+  EPI_BIAS_RES_STATS = 3, // out = acc (+ bias) + residual; partial (sum,sumsq)    -> bf16   (ViT out_proj/fc2, LLaMA o/down)
+  EPI_RMS_QKV_ROPE = 4,   // v = rstd*acc; RoPE on q,k; q -> qbuf, k,v -> KV cache -> bf16   (LLaMA prefill QKV)
+  EPI_RMS_SWIGLU = 5,     // silu(rstd*acc[2j]) * (rstd*acc[2j+1])                 -> bf16   (LLaMA gate/up)
+  EPI_RMS_F32 = 6,        // out = rstd*acc                                        -> fp32   (lm_head logits)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles;
+  void* out;
+  long long ldo;                  // output row stride in elements
+  const float* bias;              // [N] fp32 or nullptr
+  const float* colsum;            // [N] fp32 (LN fold)
+  const float2* stats_in;         // [M, stats_in_nt] partial (sum, sumsq) of the A rows
+  int stats_in_nt;
+  float inv_dim;                  // 1 / K_logical (row length the statistics are over)
+  float eps;
+  float2* stats_out;              // [M, num_n_tiles] partial (sum, sumsq) of the bf16-rounded output rows
+  const __nv_bfloat16* residual;  // [M, ldr]
+  long long ldr;
+  // EPI_RMS_QKV_ROPE
+  const float2* rope;             // [max_pos, 64] (cos, sin), bf16-rounded values
+  int S, past, H, nH, Smax;       // row m -> (b = m / S, s = m % S), position = past + s
+  __nv_bfloat16* kcache;          // [B, nH, Smax, 128] for this layer
+  __nv_bfloat16* vcache;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;                        // 2 accumulator stages (256 or 512)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int THREADS = 192;
+};
+
+VLY_DEVINL float quick_gelu_f(float v) { return v * __frcp_rn(1.0f + __expf(-1.702f * v)); }
+VLY_DEVINL float silu_f(float v) { return v * __frcp_rn(1.0f + __expf(-v)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(base_u32 + stage * Cfg::A_BYTES, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(base_u32 + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 K-elements = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[stage]);                    // frees this smem stage when the MMAs retire
+          if (kb == num_kb - 1) tc_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r_in_tile = quad * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      const int row = m_blk * BM + r_in_tile;
+      const bool row_ok = row < p.M;
+
+      float mean = 0.f, rstd = 1.f;
+      if constexpr (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU || EPI == EPI_RMS_QKV_ROPE || EPI == EPI_RMS_SWIGLU ||
+                    EPI == EPI_RMS_F32) {
+        if (row_ok) {
+          float s = 0.f, ss = 0.f;
+          const float2* st = p.stats_in + (size_t)row * p.stats_in_nt;
+          for (int i = 0; i < p.stats_in_nt; ++i) {
+            const float2 v = st[i];
+            s += v.x;
+            ss += v.y;
+          }
+          if constexpr (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU) {
+            mean = s * p.inv_dim;
+            const float var = fmaxf(ss * p.inv_dim - mean * mean, 0.f);
+            rstd = rsqrtf(var + p.eps);
+          } else {
+            rstd = rsqrtf(ss * p.inv_dim + p.eps);
+          }
+        }
+      }
+      int b_idx = 0, pos = 0;
+      if constexpr (EPI == EPI_RMS_QKV_ROPE) {
+        if (row_ok) {
+          b_idx = row / p.S;
+          pos = p.past + (row % p.S);
+        }
+      }
+
+      __syncwarp();
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      float st_sum = 0.f, st_sq = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * BN + c * 32, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (row_ok && n0 < p.N) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+
+        if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_RES_STATS) {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+          }
+        }
+        if constexpr (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float cs = __ldg(p.colsum + n0 + i), bb = __ldg(p.bias + n0 + i);
+            float t = rstd * (v[i] - mean * cs) + bb;
+            if constexpr (EPI == EPI_LN_BIAS_GELU) t = quick_gelu_f(t);
+            v[i] = t;
+          }
+        }
+        if constexpr (EPI == EPI_RMS_QKV_ROPE || EPI == EPI_RMS_SWIGLU || EPI == EPI_RMS_F32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= rstd;
+        }
+
+        if constexpr (EPI == EPI_BIAS_RES_STATS) {
+          // residual add, bf16 rounding, partial row statistics of the ROUNDED values
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0);
+          uint4 o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 rr = __ldg(rp + j);
+            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float a = v[j * 8 + t * 2] + bf16_lo(rw[t]);
+              const float b = v[j * 8 + t * 2 + 1] + bf16_hi(rw[t]);
+              ow[t] = pack_bf16x2(a, b);
+              const float ar = bf16_lo(ow[t]), br = bf16_hi(ow[t]);
+              st_sum += ar + br;
+              st_sq += ar * ar + br * br;
+            }
+            o[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = o[j];
+        } else if constexpr (EPI == EPI_RMS_SWIGLU) {
+          uint32_t ow[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float a = silu_f(v[4 * j]) * v[4 * j + 1];
+            const float b = silu_f(v[4 * j + 2]) * v[4 * j + 3];
+            ow[j] = pack_bf16x2(a, b);
+          }
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + (n0 >> 1));
+          op[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          op[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        } else if constexpr (EPI == EPI_RMS_F32) {
+          float* op = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + n0;
+          if (n0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i < p.N) op[i] = v[i];
+          }
+        } else if constexpr (EPI == EPI_RMS_QKV_ROPE) {
+          const int which = n0 / p.H;            // 0 q, 1 k, 2 v (uniform over the chunk: H % 32 == 0)
+          const int nh = n0 - which * p.H;
+          const int head = nh >> 7, cidx = nh & 127;
+          if (which < 2) {
+            // interleaved layout: columns (2j, 2j+1) hold original dims (j, j+64) of the head
+            const float2* cs = p.rope + (size_t)pos * 64 + (cidx >> 1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 c_s = __ldg(cs + j);
+              const float x0 = v[2 * j], x1 = v[2 * j + 1];
+              v[2 * j] = x0 * c_s.x - x1 * c_s.y;
+              v[2 * j + 1] = x1 * c_s.x + x0 * c_s.y;
+            }
+          }
+          __nv_bfloat16* dst;
+          if (which == 0) {
+            dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + nh;
+          } else {
+            __nv_bfloat16* cache = (which == 1) ? p.kcache : p.vcache;
+            dst = cache + (((size_t)b_idx * p.nH + head) * p.Smax + pos) * 128 + cidx;
+          }
+          uint4* op = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+          // EPI_BIAS / EPI_LN_BIAS / EPI_LN_BIAS_GELU -> bf16 rows
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n0;
+          if (n0 + 32 <= p.N && (p.ldo & 7) == 0) {
+            uint4* op = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i < p.N) dst[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+        }  // row_ok && n0 < N
+      }
+      __syncwarp();
+      // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+      if constexpr (EPI == EPI_BIAS_RES_STATS) {
+        if (row_ok && p.stats_out != nullptr)
+          p.stats_out[(size_t)row * p.num_n_tiles + n_blk] = make_float2(st_sum, st_sq);
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace vly

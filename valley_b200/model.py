@@ -1,0 +1,525 @@
+"""Reference-facing Python surface: the same class / method names, argument meaning and error
+behaviour as valley/model/valley_model.py, with every tensor op executed by libvalley_b200.so.
+
+    ValleyConfig                      valley_model.py:18
+    ValleyLlamaModel                  valley_model.py:21   (.vision_tower.config sentinel ids, .forward)
+    ValleyLlamaForCausalLM            valley_model.py:257  (.forward, .get_model, .generate,
+                                      .prepare_inputs_for_generation, .build_inputs, .process_response)
+  + encode_images / prepare_inputs_labels_for_multimodal: the two inline blocks valley_model.py:163-190
+    and :192-247 factored out under the names BASELINE.json's north_star uses.
+
+PyTorch is used here only for device memory, streams and (optionally) sampling; there is no
+eager / CPU fallback for any op on the path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import types
+from typing import Iterable, List, Optional, Tuple, Union
+
+import torch
+
+from . import _lib
+from ._lib import VlyConfig, VlyTokens, check
+
+# valley/util/config.py:1-13
+IGNORE_INDEX = -100
+DEFAULT_IMAGE_PATCH_TOKEN = "<im_patch>"
+DEFAULT_IM_START_TOKEN = "<im_start>"
+DEFAULT_IM_END_TOKEN = "<im_end>"
+DEFAULT_VIDEO_FRAME_TOKEN = "<vi_frame>"
+DEFAULT_VI_START_TOKEN = "<vi_start>"
+DEFAULT_VI_END_TOKEN = "<vi_end>"
+
+_DT = {torch.float32: _lib.VLY_F32, torch.bfloat16: _lib.VLY_BF16, torch.float16: _lib.VLY_F16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class ValleyConfig:
+    """ValleyConfig(LlamaConfig), model_type 'valley' (valley_model.py:18-19) plus the extra keys the reference
+    reads: mm_vision_tower, use_mm_proj, mm_hidden_size, mm_vision_select_layer, mm_use_im_start_end."""
+    model_type = "valley"
+
+    def __init__(self, hidden_size=4096, num_hidden_layers=32, num_attention_heads=32, intermediate_size=11008,
+                 vocab_size=32008, rms_norm_eps=1e-5, rope_theta=10000.0, max_position_embeddings=2048,
+                 mm_vision_tower="openai/clip-vit-large-patch14", mm_hidden_size=1024, mm_vision_select_layer=-2,
+                 use_mm_proj=True, mm_use_im_start_end=True, vit_layers=24, vit_heads=16, vit_mlp=4096, vit_patch=14,
+                 vit_image=224, vit_eps=1e-5, **kw):
+        self.hidden_size, self.num_hidden_layers = hidden_size, num_hidden_layers
+        self.num_attention_heads, self.intermediate_size = num_attention_heads, intermediate_size
+        self.vocab_size, self.rms_norm_eps, self.rope_theta = vocab_size, rms_norm_eps, rope_theta
+        self.max_position_embeddings = max_position_embeddings
+        self.mm_vision_tower, self.mm_hidden_size = mm_vision_tower, mm_hidden_size
+        self.mm_vision_select_layer, self.use_mm_proj = mm_vision_select_layer, use_mm_proj
+        self.mm_use_im_start_end = mm_use_im_start_end
+        self.vit_layers, self.vit_heads, self.vit_mlp = vit_layers, vit_heads, vit_mlp
+        self.vit_patch, self.vit_image, self.vit_eps = vit_patch, vit_image, vit_eps
+        self.use_return_dict, self.use_cache = True, True
+        self.output_attentions = self.output_hidden_states = False
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @classmethod
+    def from_spec(cls, spec, **kw):
+        return cls(hidden_size=spec.hidden_size, num_hidden_layers=spec.num_hidden_layers,
+                   num_attention_heads=spec.num_attention_heads, intermediate_size=spec.intermediate_size,
+                   vocab_size=spec.vocab_size, rms_norm_eps=spec.rms_norm_eps, rope_theta=spec.rope_theta,
+                   max_position_embeddings=spec.max_position_embeddings, mm_hidden_size=spec.vit_hidden,
+                   mm_vision_select_layer=spec.mm_vision_select_layer, vit_layers=spec.vit_layers,
+                   vit_heads=spec.vit_heads, vit_mlp=spec.vit_mlp, vit_patch=spec.vit_patch,
+                   vit_image=spec.vit_image, vit_eps=spec.vit_eps, **kw)
+
+
+class CausalLMOutputWithPast(dict):
+    """Attribute + index access like transformers.modeling_outputs.CausalLMOutputWithPast."""
+
+    def __init__(self, loss=None, logits=None, past_key_values=None, hidden_states=None, attentions=None):
+        super().__init__(loss=loss, logits=logits, past_key_values=past_key_values,
+                         hidden_states=hidden_states, attentions=attentions)
+        self.__dict__ = self
+
+    def __getitem__(self, k):
+        if isinstance(k, int):
+            return [v for v in (self.loss, self.logits, self.past_key_values) if v is not None][k]
+        return dict.__getitem__(self, k)
+
+
+class _ShapeOnly:
+    def __init__(self, shape):
+        self.shape = torch.Size(shape)
+
+
+class ValleyKVCache:
+    """Opaque KV cache returned as ``past_key_values``.  Supports both access patterns callers use:
+    ``past_key_values[0][0].shape[-2]`` (model_worker.py:253, :381, pinned-HF tuple cache) and
+    ``.get_seq_length()`` (HF >= 4.36 DynamicCache).  Storage is the library's pre-allocated
+    [L][2][B][heads][max_seq][128] bf16 buffer, appended in place by the QKV epilogues."""
+
+    def __init__(self, model: "ValleyLlamaForCausalLM", batch: int, max_seq: int):
+        self._model, self.batch, self.max_seq = model, batch, max_seq
+        h = C.c_void_p()
+        check(model._lib.vly_kv_create(model._ctx, batch, max_seq, C.byref(h)))
+        self._h = h
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        n = C.c_int()
+        check(self._model._lib.vly_kv_seq_len(self._h, C.byref(n)))
+        return n.value
+
+    def __len__(self):
+        return self._model.config.num_hidden_layers
+
+    def __bool__(self):
+        return True
+
+    def __getitem__(self, layer):
+        c = self._model.config
+        shp = (self.batch, c.num_attention_heads, self.get_seq_length(), c.hidden_size // c.num_attention_heads)
+        return (_ShapeOnly(shp), _ShapeOnly(shp))
+
+    def to_hf(self, layer: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Materialise layer's (key, value) in HuggingFace layout [B, heads, len, 128] (keys de-interleaved)."""
+        c, n = self._model.config, self.get_seq_length()
+        out = []
+        for which in (0, 1):
+            t = torch.empty(self.batch, c.num_attention_heads, n, 128, dtype=torch.bfloat16, device=self._model.device)
+            check(self._model._lib.vly_kv_export(self._model._ctx, self._h, layer, which, t.data_ptr(), _stream()))
+            out.append(t)
+        return tuple(out)
+
+    def reset(self):
+        check(self._model._lib.vly_kv_reset(self._h, _stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._model._ctx:
+                self._model._lib.vly_kv_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class _VisionTower:
+    """Stands where CLIPVisionModel sits on the reference model: carries ``.config`` with the sentinel ids
+    (run_valley.py:13-18, model_worker.py:80-84) and is callable like the reference's use of it."""
+
+    def __init__(self, model: "ValleyLlamaForCausalLM"):
+        self._model = model
+        cfg = model.config
+        self.config = types.SimpleNamespace(
+            hidden_size=cfg.mm_hidden_size, image_size=cfg.vit_image, patch_size=cfg.vit_patch,
+            num_hidden_layers=cfg.vit_layers, use_im_start_end=cfg.mm_use_im_start_end,
+            im_patch_token=-1, im_start_token=-1, im_end_token=-1)
+
+    def __call__(self, pixel_values: torch.Tensor, output_hidden_states: bool = True, select_layer: Optional[int] = None):
+        sel = self._model.config.mm_vision_select_layer if select_layer is None else select_layer
+        hs = self._model._vit_encode(pixel_values, sel)
+        return types.SimpleNamespace(selected_hidden_state=hs, select_layer=sel)
+
+
+class ValleyLlamaModel:
+    """valley_model.py:21-254.  Holds the vision tower handle; ``forward`` returns final hidden states is NOT exposed
+    separately (the final RMSNorm is folded into lm_head) -- callers in the reference only use the CausalLM wrapper."""
+
+    def __init__(self, owner: "ValleyLlamaForCausalLM"):
+        self._owner = owner
+        self.config = owner.config
+        self.vision_tower = _VisionTower(owner)
+        self.patch_pooling_method = "mean"          # valley_model.py:27
+        self.mm_projector = types.SimpleNamespace(in_features=owner.config.mm_hidden_size,
+                                                  out_features=owner.config.hidden_size)
+        self.embed_tokens = types.SimpleNamespace(num_embeddings=owner.config.vocab_size,
+                                                  embedding_dim=owner.config.hidden_size)
+
+
+class ValleyLlamaForCausalLM:
+    """valley_model.py:257-439 behind libvalley_b200.so."""
+    config_class = ValleyConfig
+
+    def __init__(self, config: ValleyConfig, device: Union[int, str, torch.device] = 0):
+        self._lib = _lib.load()
+        self._ctx = None
+        self.config = config
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise _lib.VlyError("valley_b200 runs on a CUDA sm_100a device only; there is no CPU path")
+        self.device = dev
+        self.dtype = torch.bfloat16
+        c = VlyConfig(config.hidden_size, config.num_hidden_layers, config.num_attention_heads, config.intermediate_size,
+                      config.vocab_size, config.rms_norm_eps, config.rope_theta, config.max_position_embeddings,
+                      config.mm_hidden_size, config.vit_layers, config.vit_heads, config.vit_mlp, config.vit_patch,
+                      config.vit_image, config.vit_eps, config.mm_vision_select_layer, dev.index or 0)
+        h = C.c_void_p()
+        check(self._lib.vly_create(C.byref(c), C.byref(h)))
+        self._ctx = h
+        self.model = ValleyLlamaModel(self)
+        self.training = False
+        self.logits_all_positions = True      # reference behaviour (valley_model.py:304-305); generate() uses last-only
+
+    # ---------------- lifetime / weights ----------------
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                self._lib.vly_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    @classmethod
+    def from_state_dict(cls, config: ValleyConfig, state: Iterable, device=0) -> "ValleyLlamaForCausalLM":
+        m = cls(config, device)
+        m.load_state_dict(state)
+        return m
+
+    def load_state_dict(self, state, strict: bool = False):
+        """Accepts a dict or an iterator of (hf_name, tensor).  Tensors may live on CPU or GPU, fp32/bf16/fp16.
+        Unknown names (post_layernorm, rotary inv_freq, position_ids...) are ignored like HF non-strict loading."""
+        items = state.items() if hasattr(state, "items") else state
+        for name, t in items:
+            if "post_layernorm" in name or name.endswith("position_ids") or name.endswith("inv_freq"):
+                continue
+            t = t.detach()
+            if t.dtype not in _DT:
+                t = t.float()
+            t = t.to(self.device).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            check(self._lib.vly_load_weight(self._ctx, name.encode(), t.data_ptr(), _DT[t.dtype], shape, t.dim()))
+        check(self._lib.vly_finalize_weights(self._ctx))
+        return self
+
+    def get_model(self) -> ValleyLlamaModel:      # valley_model.py:269
+        return self.model
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def launches(self) -> int:
+        n = C.c_int64()
+        check(self._lib.vly_kernel_launch_count(self._ctx, C.byref(n)))
+        return n.value
+
+    # ---------------- vision ----------------
+    def _tokens(self) -> VlyTokens:
+        vc = self.model.vision_tower.config
+        g = lambda k: int(getattr(vc, k, -1) if getattr(vc, k, None) is not None else -1)
+        return VlyTokens(g("im_patch_token"), g("im_start_token"), g("im_end_token"),
+                         g("vi_frame_token"), g("vi_start_token"), g("vi_end_token"))
+
+    def _vit_encode(self, pixels: torch.Tensor, select_layer: int) -> torch.Tensor:
+        """[F,3,224,224] -> hidden_states[select_layer] [F,257,1024] bf16."""
+        if pixels.dim() != 4 or pixels.shape[1] != 3 or pixels.shape[2] != self.config.vit_image or pixels.shape[3] != self.config.vit_image:
+            # HF:modeling_clip.py:203-207
+            raise ValueError(f"Input image size ({pixels.shape[-2]}*{pixels.shape[-1]}) doesn't match model "
+                             f"({self.config.vit_image}*{self.config.vit_image}).")
+        if pixels.dtype not in _DT:
+            pixels = pixels.float()
+        pixels = pixels.to(self.device, non_blocking=True).contiguous()
+        tokens = (self.config.vit_image // self.config.vit_patch) ** 2 + 1
+        out = torch.empty(pixels.shape[0], tokens, self.config.mm_hidden_size, dtype=torch.bfloat16, device=self.device)
+        check(self._lib.vly_vit_encode(self._ctx, pixels.data_ptr(), _DT[pixels.dtype], pixels.shape[0], select_layer,
+                                       out.data_ptr(), _stream()))
+        return out
+
+    def encode_frames(self, pixels: torch.Tensor) -> torch.Tensor:
+        """Vision tower only: [F,3,224,224] -> [F,257,1024] (config.mm_vision_select_layer)."""
+        return self._vit_encode(pixels, getattr(self.config, "mm_vision_select_layer", -1))
+
+    def _project(self, feats: torch.Tensor) -> torch.Tensor:
+        rows = feats.numel() // feats.shape[-1]
+        out = torch.empty(*feats.shape[:-1], self.config.hidden_size, dtype=torch.bfloat16, device=self.device)
+        check(self._lib.vly_project(self._ctx, feats.data_ptr(), rows, out.data_ptr(), _stream()))
+        return out
+
+    @torch.no_grad()
+    def encode_images(self, images):
+        """valley_model.py:163-190: tensor [B,T,3,H,W] -> [B,T,257,hidden]; list of [T_i,3,H,W] -> list."""
+        if isinstance(images, (list, tuple)):
+            return [self._project(self.encode_frames(img)) for img in images]
+        B, T = images.shape[:2]
+        feats = self.encode_frames(images.reshape(B * T, *images.shape[2:]))
+        return self._project(feats).view(B, T, feats.shape[1], self.config.hidden_size)
+
+    def _pool_project(self, feats: torch.Tensor, n_videos: int, T: int) -> torch.Tensor:
+        """feats [n_videos*T,257,1024] -> [n_videos, 256+T, hidden] (pool-first)."""
+        rows = feats.shape[1] - 1 + T
+        out = torch.empty(n_videos, rows, self.config.hidden_size, dtype=torch.bfloat16, device=self.device)
+        check(self._lib.vly_pool_project(self._ctx, feats.data_ptr(), n_videos, T, out.data_ptr(), _stream()))
+        return out
+
+    def _splice_plan(self, input_ids: torch.Tensor, T: int):
+        ids = input_ids.detach().to("cpu", torch.int64).contiguous()
+        B, S = ids.shape
+        smap = torch.empty(B, S, dtype=torch.int32)
+        iidx = torch.empty(B, dtype=torch.int32)
+        tok = self._tokens()
+        check(self._lib.vly_build_splice_map(C.cast(ids.data_ptr(), C.POINTER(C.c_int64)), B, S, T, C.byref(tok),
+                                             C.cast(smap.data_ptr(), C.POINTER(C.c_int32)),
+                                             C.cast(iidx.data_ptr(), C.POINTER(C.c_int32))))
+        return smap, iidx
+
+    @torch.no_grad()
+    def prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask=None, past_key_values=None, labels=None,
+                                              images=None, frame_features: Optional[torch.Tensor] = None,
+                                              n_frames: Optional[int] = None):
+        """valley_model.py:155-247 -> (None, attention_mask, past_key_values, inputs_embeds, labels).
+
+        Vision runs iff input_ids.shape[1] != 1 (or training) and images is not None (:163-164).
+        ``frame_features`` ([n_videos*n_frames,257,1024], e.g. all-gathered from other ranks) skips the local ViT."""
+        B, S = input_ids.shape
+        ids_dev = input_ids.to(self.device, torch.int64).contiguous()
+        embeds = torch.empty(B, S, self.config.hidden_size, dtype=torch.bfloat16, device=self.device)
+        use_vision = (images is not None or frame_features is not None) and (S != 1 or self.training)
+        if not use_vision:
+            check(self._lib.vly_embed_splice(self._ctx, ids_dev.data_ptr(), None, None, None, 0, B, S, embeds.data_ptr(), _stream()))
+            return None, attention_mask, past_key_values, embeds, labels
+        if isinstance(images, (list, tuple)):
+            # variable T per sample (valley_model.py:168-176): plan and pool per sample
+            vis, smaps, cur = [], [], 0
+            for b in range(B):
+                T_b = images[min(cur, len(images) - 1)].shape[0]
+                smap, iidx = self._splice_plan(input_ids[b:b + 1], T_b)
+                if iidx[0] >= 0:
+                    feats = self.encode_frames(images[cur])
+                    vis.append(self._pool_project(feats, 1, T_b)[0])
+                    cur += 1
+                smaps.append((smap, int(iidx[0])))
+            out = []
+            for b, (smap, flag) in enumerate(smaps):
+                e = torch.empty(1, S, self.config.hidden_size, dtype=torch.bfloat16, device=self.device)
+                if flag < 0:
+                    check(self._lib.vly_embed_splice(self._ctx, ids_dev[b:b + 1].data_ptr(), None, None, None, 0, 1, S, e.data_ptr(), _stream()))
+                else:
+                    v = vis.pop(0).contiguous()
+                    sm = smap.to(self.device)
+                    z = torch.zeros(1, dtype=torch.int32, device=self.device)
+                    check(self._lib.vly_embed_splice(self._ctx, ids_dev[b:b + 1].data_ptr(), sm.data_ptr(), z.data_ptr(), v.data_ptr(),
+                                                     v.shape[0], 1, S, e.data_ptr(), _stream()))
+                out.append(e)
+            return None, attention_mask, past_key_values, torch.cat(out, 0), labels
+        if frame_features is None:
+            Bi, T = images.shape[:2]
+            frame_features = self.encode_frames(images.reshape(Bi * T, *images.shape[2:]))
+        else:
+            T = n_frames if n_frames is not None else images.shape[1]
+            Bi = frame_features.shape[0] // T
+        smap, iidx = self._splice_plan(input_ids, T)          # raises ValueError exactly where the reference does
+        vis = self._pool_project(frame_features, Bi, T)        # [Bi, 256+T, H]
+        n_mm = int((iidx >= 0).sum())
+        if n_mm > Bi:
+            raise IndexError("index out of range: more multimodal samples than images")   # image_features[cur_image_idx]
+        sm, ii = smap.to(self.device, non_blocking=True), iidx.clamp(min=0).to(self.device, non_blocking=True)
+        check(self._lib.vly_embed_splice(self._ctx, ids_dev.data_ptr(), sm.data_ptr(), ii.data_ptr(), vis.data_ptr(), vis.shape[1],
+                                         B, S, embeds.data_ptr(), _stream()))
+        return None, attention_mask, past_key_values, embeds, labels
+
+    # ---------------- language model ----------------
+    def new_cache(self, batch: int, max_seq: Optional[int] = None) -> ValleyKVCache:
+        return ValleyKVCache(self, batch, max_seq or self.config.max_position_embeddings)
+
+    def _prefill(self, cache: ValleyKVCache, embeds: torch.Tensor, logits_mode: int):
+        B, S, _ = embeds.shape
+        V = self.config.vocab_size
+        logits = None
+        if logits_mode == 2:
+            logits = torch.empty(B, S, V, dtype=torch.float32, device=self.device)
+        elif logits_mode == 1:
+            logits = torch.empty(B, 1, V, dtype=torch.float32, device=self.device)
+        nxt = torch.empty(B, dtype=torch.int64, device=self.device)
+        check(self._lib.vly_llama_prefill(self._ctx, cache._h, embeds.data_ptr(), B, S, logits_mode, _ptr(logits), nxt.data_ptr(), _stream()))
+        return logits, nxt
+
+    def _decode(self, cache: ValleyKVCache, tokens: torch.Tensor, want_logits: bool):
+        B = tokens.shape[0]
+        nxt = torch.empty(B, dtype=torch.int64, device=self.device)
+        logits = torch.empty(B, 1, self.config.vocab_size, dtype=torch.float32, device=self.device) if want_logits else None
+        tk = tokens.reshape(B).to(self.device, torch.int64).contiguous()
+        check(self._lib.vly_llama_decode(self._ctx, cache._h, tk.data_ptr(), nxt.data_ptr(), _ptr(logits), _stream()))
+        return logits, nxt
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, images=None, return_dict=None):
+        """ValleyLlamaForCausalLM.forward (valley_model.py:272-330).  logits are fp32 [B,S,V]
+        (the reference returns them in the model dtype; callers .float() them).  attention_mask is accepted and,
+        as on the reference's own inference paths (all-ones masks, model_worker.py:380-385), not applied."""
+        if inputs_embeds is None:
+            if input_ids is None:
+                raise ValueError("You have to specify either input_ids or inputs_embeds")
+            _, _, _, inputs_embeds, _ = self.prepare_inputs_labels_for_multimodal(
+                input_ids, attention_mask, past_key_values, labels, images)
+        else:
+            if images is not None and input_ids is None:
+                # the reference dereferences input_ids.shape here (valley_model.py:164)
+                raise AttributeError("'NoneType' object has no attribute 'shape'")
+            inputs_embeds = inputs_embeds.to(self.device, torch.bfloat16).contiguous()
+        B, S, _ = inputs_embeds.shape
+        cache = past_key_values if isinstance(past_key_values, ValleyKVCache) else None
+        if cache is None:
+            cache = self.new_cache(B)
+        if S == 1 and cache.get_seq_length() > 0 and input_ids is not None:
+            logits, nxt = self._decode(cache, input_ids, True)
+        else:
+            logits, nxt = self._prefill(cache, inputs_embeds, 2 if self.logits_all_positions else 1)
+        loss = None
+        if labels is not None:       # valley_model.py:308-318
+            sl = logits[..., :-1, :].reshape(-1, self.config.vocab_size)
+            tl = labels.to(self.device)[..., 1:].reshape(-1)
+            loss = torch.nn.functional.cross_entropy(sl, tl, ignore_index=IGNORE_INDEX)
+        out = CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=cache)
+        out.next_tokens = nxt
+        if return_dict is False:
+            return tuple(v for v in (loss, logits, cache) if v is not None)
+        return out
+
+    __call__ = forward
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None, **kwargs):
+        """valley_model.py:332-352 with the INTENDED semantics: slice to the last token only
+        once the cache actually holds tokens."""
+        if past_key_values is not None and (not hasattr(past_key_values, "get_seq_length") or past_key_values.get_seq_length() > 0):
+            input_ids = input_ids[:, -1:]
+        if inputs_embeds is not None and past_key_values is None:
+            model_inputs = {"inputs_embeds": inputs_embeds}
+        else:
+            model_inputs = {"input_ids": input_ids}
+        model_inputs.update({"past_key_values": past_key_values, "use_cache": kwargs.get("use_cache"),
+                             "attention_mask": attention_mask, "images": kwargs.get("images", None)})
+        return model_inputs
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, images=None, max_new_tokens: int = 1024, do_sample: bool = False,
+                 temperature: float = 1.0, stopping_criteria=None, eos_token_id: Optional[int] = None, **kw):
+        """Greedy (or temperature) generation == the loop of model_worker.py:371-397 / HF generate as called at
+        valley_model.py:432.  Returns [B, S + n_new] like HF.  With no stopping criteria, greedy decoding runs
+        entirely on the device (CUDA-graph replay, no per-token host sync)."""
+        B, S = input_ids.shape
+        room = self.config.max_position_embeddings - S
+        n_new = max(0, min(max_new_tokens, room))
+        if n_new == 0:
+            return input_ids.to(self.device)
+        cache = self.new_cache(B)
+        _, _, _, embeds, _ = self.prepare_inputs_labels_for_multimodal(input_ids, None, None, None, images)
+        greedy = (not do_sample) or temperature < 1e-4
+        logits, nxt = self._prefill(cache, embeds, 0 if greedy else 1)
+        ids_dev = input_ids.to(self.device, torch.int64)
+        if greedy and not stopping_criteria and eos_token_id is None:
+            out = torch.empty(B, n_new, dtype=torch.int64, device=self.device)
+            out[:, 0] = nxt
+            if n_new > 1:
+                rest = torch.empty(B, n_new - 1, dtype=torch.int64, device=self.device)
+                check(self._lib.vly_generate_greedy(self._ctx, cache._h, nxt.data_ptr(), n_new - 1, rest.data_ptr(), _stream()))
+                out[:, 1:] = rest
+            return torch.cat([ids_dev, out], dim=1)
+        # host-visible loop (stopping criteria / sampling / eos): one device->host sync per token, as in the reference
+        seq = ids_dev
+        for i in range(n_new):
+            if not greedy:
+                probs = torch.softmax(logits[:, -1, :] / temperature, dim=-1)    # model_worker.py:393-394
+                nxt = torch.multinomial(probs, num_samples=1).reshape(B)
+            seq = torch.cat([seq, nxt[:, None]], dim=1)
+            if eos_token_id is not None and bool((nxt == eos_token_id).all()):
+                break
+            if stopping_criteria and any(sc(seq, None) for sc in stopping_criteria):
+                break
+            if i + 1 < n_new:
+                logits, nxt = self._decode(cache, nxt, not greedy)
+        return seq
+
+    # ---------------- prompt helpers (pure string logic; valley_model.py:381-422) ----------------
+    def build_inputs(self, tokenizer, messages):
+        prompt = ''
+        for m in messages:
+            if m['role'] == 'system':
+                prompt += m['content'] + '\n\n' + '###'
+            elif m['role'] == 'user':
+                replace_token = DEFAULT_IM_START_TOKEN + DEFAULT_IMAGE_PATCH_TOKEN * 256 + DEFAULT_IM_END_TOKEN + \
+                    DEFAULT_VI_START_TOKEN + DEFAULT_VIDEO_FRAME_TOKEN * 8 + DEFAULT_VI_END_TOKEN
+                if '<video>' in m['content'] or '<image>' in m['content']:
+                    message = m['content'].replace('<video>', replace_token).replace('<image>', replace_token)
+                    prompt += ' ' + 'Human' + ": " + message + ' \n' + '###'
+            elif m['role'] == 'assistent':
+                prompt += ' ' + 'Assistent' + ": " + m['content'] + ' \n' + '###'
+            else:
+                raise ValueError("Role is only suport \"assistent\", \"human\" and \"system\".")
+        if DEFAULT_IM_START_TOKEN not in prompt:
+            raise ValueError("You need to specify the <video> token in the query")
+        tokenizer.padding_side = 'left'
+        return tokenizer([prompt], padding=True)
+
+    def process_response(self, outputs):
+        output = []
+        for out in outputs:
+            while True:
+                cur_len = len(out)
+                out = out.strip()
+                for pattern in ['###', 'Assistant:', 'Response:', 'Valley:']:
+                    if out.startswith(pattern):
+                        out = out[len(pattern):].strip()
+                if len(out) == cur_len:
+                    break
+            if '###' not in out:
+                out += '###'
+            output.append(out[:out.index('###')].strip())
+        return output
+
+    @torch.no_grad()
+    def completion(self, tokenizer, video, message: list, gen_kwargs: dict, device=None):
+        """valley_model.py:424-439.  ``video`` is a [3,T,224,224] tensor (what load_video returns) -- decoding a file
+        with decord is outside the hot path."""
+        inputs = self.build_inputs(tokenizer, message)
+        input_ids = torch.as_tensor(inputs.input_ids).to(self.device)
+        if not torch.is_tensor(video):
+            raise TypeError("completion() takes the decoded clip tensor [3,T,224,224]; file decoding is out of scope")
+        images = video.permute(1, 0, 2, 3).unsqueeze(0).half().to(self.device)
+        output_ids = self.generate(input_ids=input_ids, images=images, **gen_kwargs)
+        n_in = input_ids.shape[1]
+        outputs = tokenizer.batch_decode(output_ids[:, n_in:], skip_special_tokens=True)
+        return self.process_response(outputs)
