@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric on BASELINE.json config[1]:
+   "8-frame 224x224 synthetic video, Valley2-7b bf16, 1xB200, greedy 128 tokens".
+
+A *step* is one request per rank through the whole hot path: ViT-L/14 encode of the video's 8 frames ->
+(N>1: all-gather of frame features) -> temporal pool + mm_projector -> splice -> LLaMA prefill -> 128 greedy
+tokens (CUDA-graph replay, no per-token host sync).  `value` = generated tokens / s over whole steps with the
+inputs resident in HBM; `e2e` = the same through ValleyLlamaForCausalLM.generate() from pinned HOST buffers
+(pixels H2D + token ids D2H inside the timed region).  ViT frames/s and steady-state decode tokens/s -- the two
+halves of BASELINE.json's metric -- are timed separately and reported with their roofline fractions.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model valley2-7b|valley-13b|tiny]
+  N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+--impl reference times the reference algorithm's CPU path (the oracle port: oracle/valley_oracle.py, plain
+PyTorch CPU ops == what the reference's HF modules execute) on this box's host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from valley_b200 import synthetic as syn  # noqa: E402
+
+GFLOP_PER_FRAME = {-2: 155.29, -1: 162.02}
+N_NEW = 128
+N_FRAMES = 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def decode_bytes_per_step(spec, B, S):
+    """Algorithmic HBM bytes of one decode step: every weight once (bf16) + KV read + KV write."""
+    H, I, V, L = spec.hidden_size, spec.intermediate_size, spec.vocab_size, spec.num_hidden_layers
+    w = 2 * (L * (4 * H * H + 3 * H * I) + V * H)
+    kv = B * S * 2 * L * H * 2 + B * 2 * L * H * 2
+    return w + kv
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm's CPU path (oracle port), bounded sample, all host threads
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_arm(spec, n_new=N_NEW, n_frames=N_FRAMES, sample_layers=2, decode_tokens=4):
+    """The reference algorithm on the host cores (oracle port == the ATen CPU ops the reference's HF modules run),
+    bounded sample.  Per phase the faster of bf16 / fp32 ON THE REAL WORKLOAD is used (bf16 GEMMs are slow on CPUs
+    without AMX / AVX512-BF16)."""
+    import dataclasses
+    from oracle import valley_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cores = torch.get_num_threads()
+    L = spec.num_hidden_layers
+    t0 = time.time()
+    name = {torch.bfloat16: "bf16", torch.float32: "fp32"}
+    S = 1 + 40 + 1 + 256 + 2 + n_frames + 1 + 24
+    sub = dataclasses.replace(spec, num_hidden_layers=sample_layers)
+    v32 = dict(syn.iter_state_dict(spec, 0, llm=False))
+    l32 = dict(syn.iter_state_dict(sub, 0, vision=False))
+    px32 = syn.make_pixels(1, n_frames, 0)[0]
+
+    def vit_time(dt, frames):
+        w = {k: v.to(dt) for k, v in v32.items()}
+        with torch.no_grad():
+            t = time.time()
+            O.vit_hidden_state(w, px32[:frames].to(dt), spec.mm_vision_select_layer, num_layers=spec.vit_layers)
+            return time.time() - t
+
+    def llm_times(dt, n_dec):
+        w = {k: v.to(dt) for k, v in l32.items()}
+        emb, one = torch.randn(1, S, spec.hidden_size).to(dt), torch.randn(1, 1, spec.hidden_size).to(dt)
+        kw = dict(n_layers=sample_layers, heads=spec.num_attention_heads, eps=spec.rms_norm_eps)
+        with torch.no_grad():
+            cache = O.KVCache(sample_layers)
+            t = time.time()
+            h = O.llama_model(w, emb, cache, **kw)
+            t_pre = time.time() - t
+            t = time.time()
+            torch.nn.functional.linear(h[:, -1:], w["lm_head.weight"])
+            t_head = time.time() - t
+            O.llama_model(w, one, cache, **kw)
+            t = time.time()
+            for _ in range(n_dec):
+                hh = O.llama_model(w, one, cache, **kw)
+            t_layers = (time.time() - t) / n_dec
+            t = time.time()
+            torch.nn.functional.linear(hh, w["lm_head.weight"]).argmax(-1)
+            t_head_dec = time.time() - t
+        return t_pre, t_head, t_layers, t_head_dec
+
+    vit_time(torch.float32, 1)                                               # first-touch warm-up
+    dt_vit = min((torch.bfloat16, torch.float32), key=lambda d: vit_time(d, 2))
+    dt_llm = min((torch.bfloat16, torch.float32), key=lambda d: sum(llm_times(d, 1)[2:]))
+    t_vit = vit_time(dt_vit, n_frames)
+    t_pre, t_head, t_layers, t_head_dec = llm_times(dt_llm, decode_tokens)
+    t_prefill = t_pre * L / sample_layers + t_head
+    t_step_dec = t_layers * L / sample_layers + t_head_dec
+    total = t_vit + t_prefill + n_new * t_step_dec
+    return dict(tokens_per_s=n_new / total, vit_frames_per_s=n_frames / t_vit, decode_tokens_per_s=1.0 / t_step_dec,
+                prefill_s=t_prefill, cores=cores, wall_s=time.time() - t0,
+                sample=f"CPU, {cores} threads, ViT in {name[dt_vit]} / LLaMA in {name[dt_llm]} (faster of bf16/fp32 per phase, probed on the "
+                       f"workload): full ViT-L/14 ({spec.vit_layers + 1 + spec.mm_vision_select_layer} layers) on {n_frames} frames; "
+                       f"LLaMA {sample_layers}/{L} layers + lm_head, prefill S={S} once and {decode_tokens} decode tokens, layer time scaled x{L // sample_layers}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="valley2-7b", choices=list(syn.SPECS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vit-sweep", action="store_true", help="also time ViT encode at F=64 and F=256")
+    a = ap.parse_args()
+    spec = syn.SPECS[a.model]
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    cfg_common = {"workload": f"{a.model}: 1 video x {N_FRAMES} frames 224x224 per GPU, prompt S={1 + 40 + 1 + 256 + 2 + N_FRAMES + 1 + 24}, greedy {N_NEW} new tokens",
+                  "batch_per_gpu": 1, "frames": N_FRAMES, "new_tokens": N_NEW,
+                  "parallelism": f"dp{a.gpus} (frames sharded over ranks, 1 all-gather of frame features, LLM replicated)",
+                  "l2": "inputs larger than L2 (13.2 GB of weights stream per decode step; ViT weights 606 MB)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        K = max(1, min(a.steps, 2))
+        vals = [cpu_reference_arm(spec) for _ in range(K)]
+        r = vals[-1]
+        v = sum(x["tokens_per_s"] for x in vals) / len(vals)
+        print(json.dumps({
+            "impl": "reference", "metric": "generated tokens/s (8-frame video request: ViT + project + prefill + 128 greedy tokens)",
+            "value": v, "unit": "tokens/s", "n_gpus": a.gpus, "steps": K, "warmup": 0, "ms_per_step": 1000.0 * N_NEW / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg_common,
+            "vit_frames_per_s": r["vit_frames_per_s"], "decode_tokens_per_s": r["decode_tokens_per_s"],
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ ours
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from valley_b200 import dist as vdist
+    from valley_b200.model import ValleyConfig, ValleyLlamaForCausalLM
+    t_load = time.time()
+    model = ValleyLlamaForCausalLM(ValleyConfig.from_spec(spec), local)
+    model.load_state_dict(syn.iter_state_dict(spec, 0, device=f"cuda:{local}"))
+    for k, v in syn.sentinel_ids(spec).items():
+        setattr(model.get_model().vision_tower.config, k, v)
+    torch.cuda.synchronize()
+    t_load = time.time() - t_load
+
+    n_videos = world                               # weak scaling: one video per GPU
+    ids_all = syn.make_prompt_ids(spec, n_videos, N_FRAMES, 0)
+    px_all = syn.make_pixels(n_videos, N_FRAMES, 0, dtype=torch.float16)     # callers send fp16 pixels (valley_model.py:430)
+    lo, hi = vdist.shard_bounds(n_videos * N_FRAMES, world, rank)
+    px_local_host = px_all.reshape(-1, 3, 224, 224)[lo:hi].contiguous().pin_memory()
+    vlo, vhi = vdist.shard_bounds(n_videos, world, rank)
+    ids_host = ids_all[vlo:vhi].contiguous().pin_memory()
+    px_dev, ids_dev = px_local_host.cuda(non_blocking=True), ids_host.cuda(non_blocking=True)
+    S = ids_all.shape[1]
+
+    def step_device():
+        if world > 1:
+            return vdist.generate_sharded(model, ids_dev, px_dev, n_videos, N_FRAMES, N_NEW)
+        return model.generate(input_ids=ids_dev, images=px_dev[None], max_new_tokens=N_NEW)[:, S:]
+
+    def step_e2e():
+        px = px_local_host.cuda(non_blocking=True)
+        ids = ids_host.cuda(non_blocking=True)
+        if world > 1:
+            out = vdist.generate_sharded(model, ids, px, n_videos, N_FRAMES, N_NEW)
+        else:
+            out = model.generate(input_ids=ids, images=px[None], max_new_tokens=N_NEW)[:, S:]
+        return out.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K, W):
+        for _ in range(W):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.launches()
+        e0.record()
+        for _ in range(K):
+            r = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / K, model.launches() - l0, r
+
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    ms_step, launches, toks = timed(step_device, a.steps, max(a.warmup, 3))
+    clocks = clk.stop() if rank == 0 else None
+    ms_e2e, _, toks_e2e = timed(step_e2e, a.steps, 1)
+
+    # ---- the two halves of the metric, timed separately on the device ----
+    def vit_only(F):
+        px = syn.make_pixels(1, F, 1, dtype=torch.float16)[0].cuda()
+        return timed(lambda: model.encode_frames(px), max(a.steps, 5), 3)[0]
+    ms_vit8 = vit_only(N_FRAMES)
+    sweep = {}
+    if a.vit_sweep:
+        for F in (64, 256):
+            sweep[str(F)] = F / (vit_only(F) / 1e3)
+
+    def decode_only():
+        cache = model.new_cache(vhi - vlo)
+        _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, px_dev[None] if world == 1 else None,
+                                                                    **({} if world == 1 else dict(frame_features=model.encode_frames(px_dev), n_frames=N_FRAMES)))
+        _, nxt = model._prefill(cache, emb, 0)
+        import ctypes as C
+        from valley_b200._lib import check
+        out = torch.empty(vhi - vlo, N_NEW, dtype=torch.int64, device="cuda")
+        def run(n):
+            check(model._lib.vly_generate_greedy(model._ctx, cache._h, nxt.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        run(8)                                    # warm-up incl. graph capture
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(N_NEW - 8)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / (N_NEW - 8), S + 8 + (N_NEW - 8) / 2
+    ms_dec, s_mid = decode_only()
+
+    def prefill_only():
+        _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, None)
+        def f():
+            cache = model.new_cache(vhi - vlo)
+            model._prefill(cache, emb, 0)
+        return timed(f, 3, 2)[0]
+    ms_prefill = prefill_only()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    B = vhi - vlo
+    value = world * B * N_NEW / (ms_step / 1e3)
+    e2e = world * B * N_NEW / (ms_e2e / 1e3)
+    dec_bytes = decode_bytes_per_step(spec, B, s_mid)
+    dec_gbs = dec_bytes / (ms_dec / 1e3) / 1e9
+    fps8 = N_FRAMES / (ms_vit8 / 1e3)
+    gf = GFLOP_PER_FRAME.get(spec.mm_vision_select_layer, 155.29) if spec.vit_layers == 24 else None
+    line = {
+        "metric": "generated tokens/s (8-frame video request: ViT + project + prefill + 128 greedy tokens)",
+        "value": value, "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, N(0,1) pixels, seeded prompt ids)",
+        "config": cfg_common,
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": int(px_local_host.numel() * 2 + ids_host.numel() * 8),
+                "d2h_bytes_per_step": int(B * N_NEW * 8), "ms_per_step": ms_e2e, "api": "ValleyLlamaForCausalLM.generate(input_ids, images) from pinned host tensors"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "decode_tokens_per_s": world * B / (ms_dec / 1e3), "decode_ms_per_token": ms_dec,
+        "vit_frames_per_s": world * fps8, "vit_ms_8_frames": ms_vit8, "prefill_ms": ms_prefill, "vit_sweep_frames_per_s": sweep,
+        "roofline": {"kernel": "decode step (gemv_kernel x5 per layer + decode_attention_kernel; weight streaming)", "bound": "hbm",
+                     "achieved": dec_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": dec_gbs / pk["hbm"], "peak_source": pk["src"],
+                     "algorithmic_bytes_per_step": dec_bytes, "traffic": None},
+        "roofline_vit": None if gf is None else {
+            "kernel": "ViT-L/14 encode (gemm_tc_kernel + vit_attention_kernel), F=8", "bound": "tensor",
+            "achieved": fps8 * gf / 1e3, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": fps8 * gf / 1e3 / pk["tf_burst"],
+            "gflop_per_frame": gf, "peak_source": pk["src"],
+            "sweep_frac": {k: v * gf / 1e3 / pk["tf_sust"] for k, v in sweep.items()}},
+        "weights_load_s": t_load,
+        "tokens_match_e2e": bool(torch.equal(toks.cpu(), toks_e2e)),
+    }
+    if not a.no_cpu_baseline:
+        r = cpu_reference_arm(spec)
+        line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                "vit_frames_per_s": r["vit_frames_per_s"], "decode_tokens_per_s": r["decode_tokens_per_s"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,242 @@
+"""GPU (-m gpu): the CUDA path through the C ABI vs the CPU oracle on identical seeded inputs.
+
+Tolerances (stated): bf16 kernels vs the fp32 oracle on bf16-representable weights:
+  rel-Frobenius <= 2e-2, and no worse than 1.5x the error of the same oracle run in torch-bf16 (floor 5e-3);
+greedy token ids exact wherever the oracle's top-1/top-2 margin exceeds 2x the max logit error;
+integer / index logic (splice plan, token rows) bit-exact."""
+import os
+
+import pytest
+import torch
+
+import helpers as Hh
+from oracle import valley_oracle as O
+from valley_b200 import _lib, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+_models = {}
+
+
+def get(spec_name, seed=0):
+    key = (spec_name, seed)
+    if key not in _models:
+        spec = syn.SPECS[spec_name]
+        sd = Hh.bf16_weights(spec, seed)
+        _models[key] = (spec, sd, Hh.build_model(spec, sd))
+    return _models[key]
+
+
+def bf16_sd(sd):
+    return {k: v.bfloat16() for k, v in sd.items()}
+
+
+def check_close(got, ref_fp32, ref_bf16=None, what=""):
+    e = Hh.rel_fro(got, ref_fp32)
+    assert not torch.isnan(got.float()).any(), what
+    assert e <= 2e-2, (what, e)
+    if ref_bf16 is not None:
+        eb = Hh.rel_fro(ref_bf16, ref_fp32)
+        assert e <= max(1.5 * eb, 5e-3), (what, e, eb)
+    return e
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (300, 512, 256, 256), (1000, 1024, 640, 256), (77, 1032, 512, 128),
+                                      (1, 256, 64, 256), (2056, 1024, 4096, 256)])
+def test_gemm_bias_and_residual(M, N, K, bn):
+    _, _, m = get("tiny")
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(m._lib.vly_test_gemm(m._ctx, a.data_ptr(), w.data_ptr(), M, N, K, 0, bias.data_ptr(), None, out.data_ptr(), bn, 0))
+    ref = a.float() @ w.float().T + bias
+    assert Hh.rel_fro(out, ref) < 4e-3
+    if N % 32 == 0:
+        res = torch.randn(M, N, device="cuda").bfloat16()
+        out2 = res.clone()
+        _lib.check(m._lib.vly_test_gemm(m._ctx, a.data_ptr(), w.data_ptr(), M, N, K, 3, bias.data_ptr(), out2.data_ptr(), out2.data_ptr(), bn, 0))
+        assert Hh.rel_fro(out2, ref + res.float()) < 4e-3
+
+
+@pytest.mark.parametrize("F", [1, 2, 37])
+def test_vit_attention_kernel(F):
+    _, _, m = get("tiny")
+    qkv = torch.randn(F * 257, 3072, device="cuda").bfloat16()
+    out = torch.zeros(F * 257, 1024, device="cuda", dtype=torch.bfloat16)
+    _lib.check(m._lib.vly_test_vit_attention(m._ctx, qkv.data_ptr(), F, out.data_ptr(), 0))
+    x = qkv.float().view(F, 257, 3, 16, 64)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(F * 257, 1024)
+    assert Hh.rel_fro(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("spec_name,F,sel", [("tiny", 1, -2), ("tiny", 5, -1), ("tiny", 3, 0), ("tiny-wide", 8, -2)])
+def test_vit_encode_vs_oracle(spec_name, F, sel):
+    spec, sd, m = get(spec_name, 1 if spec_name == "tiny-wide" else 0)
+    px = syn.make_pixels(1, F, 3)[0]
+    got = m._vit_encode(px.cuda(), sel)
+    with torch.no_grad():
+        ref = O.vit_hidden_state(sd, px, sel, num_layers=spec.vit_layers)
+        ref_bf = O.vit_hidden_state(bf16_sd(sd), px.bfloat16(), sel, num_layers=spec.vit_layers)
+    check_close(got, ref, ref_bf, f"vit[{sel}]")
+    # pixel dtype variants the callers send (fp16: valley_model.py:430)
+    got16 = m._vit_encode(px.half().cuda(), sel)
+    assert Hh.rel_fro(got16, got) < 1e-2
+
+
+def test_vit_frames_are_independent_and_chunking_is_invisible():
+    spec, sd, m = get("tiny")
+    px = syn.make_pixels(1, 7, 9)[0].cuda()
+    full = m.encode_frames(px)
+    parts = torch.cat([m.encode_frames(px[:3]), m.encode_frames(px[3:])])
+    assert torch.equal(full, parts)                      # same kernels, same tiles per frame -> bit-identical
+
+
+def test_vit_rejects_wrong_image_size():
+    _, _, m = get("tiny")
+    with pytest.raises(ValueError):
+        m.encode_frames(torch.zeros(1, 3, 196, 196, device="cuda"))
+
+
+def test_encode_images_and_splice_vs_oracle():
+    spec, sd, m = get("tiny")
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    B, T = 2, 3
+    ids, px = syn.make_prompt_ids(spec, B, T, 0), syn.make_pixels(B, T, 0)
+    with torch.no_grad():
+        ref_enc = O.encode_images(sd, px, cfg.mm_vision_select_layer, num_layers=cfg.vit_layers)
+        ref_emb = O.prepare_inputs_embeds(sd, ids, ref_enc, tok)
+    enc = m.encode_images(px.cuda())
+    assert enc.shape == ref_enc.shape
+    check_close(enc, ref_enc, None, "encode_images")
+    r = m.prepare_inputs_labels_for_multimodal(ids.cuda(), None, None, None, px.cuda())
+    assert r[0] is None and r[3].shape == ref_emb.shape
+    check_close(r[3], ref_emb, None, "inputs_embeds")
+    text = ids[0] < spec.vocab_size - 6
+    assert torch.equal(r[3][0][text.cuda()].float().cpu(), ref_emb[0][text])     # gathered token rows: bit-exact
+    # list-of-tensors input with different T per sample (valley_model.py:168-176)
+    lst = [px[0, :2].cuda(), px[1].cuda()]
+    ids2 = torch.stack([syn.make_prompt_ids(spec, 1, 3, 0)[0], syn.make_prompt_ids(spec, 1, 3, 1)[0]])
+    ids2[0] = syn.make_prompt_ids(spec, 1, 3, 0)[0]
+    r2 = m.prepare_inputs_labels_for_multimodal(ids2[1:].cuda(), None, None, None, [lst[1]])
+    with torch.no_grad():
+        e1 = O.prepare_inputs_embeds(sd, ids2[1:], O.encode_images(sd, [px[1]], cfg.mm_vision_select_layer, num_layers=cfg.vit_layers), tok)
+    check_close(r2[3], e1, None, "list input")
+
+
+def test_splice_golden_cases_and_errors_through_the_model():
+    spec, sd, m = get("tiny")
+    g = torch.load(os.path.join(GOLD, "ref_tiny.pt"))
+    px = syn.make_pixels(g["B"], g["T"], g["seed"])
+    fp32_sd = syn.make_state_dict(spec, g["seed"])
+    for case, d in g["splice"].items():
+        cpx = px[:1, : d["n_frames"]]
+        emb = m.prepare_inputs_labels_for_multimodal(d["ids"].cuda(), None, None, None, cpx.cuda())[3]
+        ref = d["embeds_sub"]                       # the REFERENCE's own inputs_embeds (fp32 weights), sub-sampled
+        assert Hh.rel_fro(emb[:, :, ::8], ref) < 2e-2, case
+    for case, d in g["errors"].items():
+        with pytest.raises(ValueError) as ei:
+            m(input_ids=d["ids"].cuda(), images=px[:1].cuda())
+        assert str(ei.value) == d["message"], case
+
+
+@pytest.mark.parametrize("spec_name,B,T", [("tiny", 2, 3), ("tiny-wide", 1, 8), ("tiny", 5, 1)])
+def test_prefill_logits_vs_oracle(spec_name, B, T):
+    spec, sd, m = get(spec_name, 1 if spec_name == "tiny-wide" else 0)
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    ids, px = syn.make_prompt_ids(spec, B, T, 0), syn.make_pixels(B, T, 0)
+    with torch.no_grad():
+        ref = O.causal_lm_forward(sd, cfg, tok, ids, px, None)
+        ref_bf = O.causal_lm_forward(bf16_sd(sd), cfg, tok, ids, px.bfloat16(), None).float()
+    out = m(input_ids=ids.cuda(), images=px.cuda())
+    assert out.logits.shape == ref.shape and out.past_key_values.get_seq_length() == ids.shape[1]
+    assert out.past_key_values[0][0].shape[-2] == ids.shape[1]            # model_worker.py:253 access pattern
+    err = check_close(out.logits, ref, ref_bf, "prefill logits")
+    # argmax must agree wherever the oracle's margin exceeds 2x the max logit error
+    max_err = (out.logits.cpu() - ref).abs().max().item()
+    top2 = ref.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * max_err
+    assert safe.float().mean() > 0.5
+    assert torch.equal(out.logits.argmax(-1).cpu()[safe], ref.argmax(-1)[safe])
+    # KV cache contents (layer 0) vs the oracle's cache
+    cache = O.KVCache(spec.num_hidden_layers)
+    with torch.no_grad():
+        O.causal_lm_forward(sd, cfg, tok, ids, px, cache)
+    k, v = out.past_key_values.to_hf(0)
+    assert Hh.rel_fro(k, cache.k[0]) < 2e-2 and Hh.rel_fro(v, cache.v[0]) < 2e-2
+
+
+def test_golden_reference_logits_and_tokens():
+    """Against the committed outputs of the reference itself (fp32 weights there, bf16 here)."""
+    for name in ("tiny", "tiny-wide"):
+        g = torch.load(os.path.join(GOLD, f"ref_{name}.pt"))
+        spec, sd, m = get(name, g["seed"])
+        ids, px = syn.make_prompt_ids(spec, g["B"], g["T"], g["seed"]), syn.make_pixels(g["B"], g["T"], g["seed"])
+        out = m(input_ids=ids.cuda(), images=px.cuda())
+        assert Hh.rel_fro(out.logits[:, -1], g["prefill_logits_last"]) < 2e-2
+        n = g["greedy_tokens"].shape[1]
+        gen = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n)[:, ids.shape[1]:].cpu()
+        top2 = g["greedy_logits"].topk(2, -1).values
+        margin = top2[..., 0] - top2[..., 1]
+        for b in range(g["B"]):
+            for i in range(n):
+                if gen[b, i] != g["greedy_tokens"][b, i]:
+                    assert margin[b, i] < 0.05, (name, b, i, margin[b, i].item())     # only near-ties may differ
+                    break
+
+
+@pytest.mark.parametrize("spec_name,B", [("tiny", 2), ("tiny", 1), ("tiny-wide", 1), ("tiny", 6)])
+def test_greedy_decode_vs_oracle(spec_name, B):
+    spec, sd, m = get(spec_name, 1 if spec_name == "tiny-wide" else 0)
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    T, n = 3, 10
+    ids, px = syn.make_prompt_ids(spec, B, T, 0), syn.make_pixels(B, T, 0)
+    with torch.no_grad():
+        r_tok, r_log = O.greedy_generate(sd, cfg, tok, ids, px, n, return_logits=True)
+    # teacher-forced through forward(past_key_values=...) exactly like model_worker.py:380-391
+    out = m(input_ids=ids.cuda(), images=px.cuda())
+    cache, logs = out.past_key_values, [out.logits[:, -1].cpu()]
+    for i in range(1, n):
+        o = m(input_ids=r_tok[:, i - 1:i].cuda(), past_key_values=cache,
+              attention_mask=torch.ones(B, cache[0][0].shape[-2] + 1, device="cuda"))
+        logs.append(o.logits[:, -1].cpu())
+        assert cache.get_seq_length() == ids.shape[1] + i
+    logs = torch.stack(logs, 1)
+    max_err = (logs - r_log).abs().max().item()
+    assert Hh.rel_fro(logs, r_log) < 2e-2
+    top2 = r_log.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * max_err
+    assert torch.equal(logs.argmax(-1)[safe], r_tok[safe])
+    # free-running device-side loop (CUDA graph): identical until the first unsafe (near-tie) position
+    gen = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n)[:, ids.shape[1]:].cpu()
+    for b in range(B):
+        for i in range(n):
+            if not safe[b, i]:
+                break
+            assert gen[b, i] == r_tok[b, i], (b, i)
+    # determinism: the same request twice gives the same ids
+    gen2 = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n)[:, ids.shape[1]:].cpu()
+    assert torch.equal(gen, gen2)
+
+
+def test_generate_host_loop_equals_device_loop_and_stops():
+    spec, sd, m = get("tiny")
+    ids, px = syn.make_prompt_ids(spec, 1, 2, 4), syn.make_pixels(1, 2, 4)
+    a = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=9)
+    stop_after = lambda seq, scores: seq.shape[1] >= ids.shape[1] + 5
+    b = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=9, stopping_criteria=[stop_after])
+    assert b.shape[1] == ids.shape[1] + 5 and torch.equal(a[:, : b.shape[1]], b)
+    c = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=4, do_sample=True, temperature=0.7)
+    assert c.shape[1] == ids.shape[1] + 4 and int(c.max()) < spec.vocab_size
+    inp = m.prepare_inputs_for_generation(a, past_key_values=None, images=px)
+    assert inp["input_ids"].shape == a.shape and inp["images"] is px
+
+
+def test_cache_capacity_is_enforced():
+    spec, sd, m = get("tiny")
+    ids = syn.make_prompt_ids(spec, 1, 2, 0)
+    cache = m.new_cache(1, 384)
+    m(input_ids=ids.cuda(), past_key_values=cache)
+    with pytest.raises(ValueError):
+        m(input_ids=ids.cuda(), past_key_values=cache)            # 2 x 327 > 384

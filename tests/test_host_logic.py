@@ -1,0 +1,128 @@
+"""CPU: the C-ABI library loads, exports every declared symbol, and its HOST logic (the exact integer
+splice plan) agrees with the oracle / the reference's golden cases.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import helpers as Hh
+from oracle import valley_oracle as O
+from valley_b200 import _lib, synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "valley_b200.h")).read()
+    declared = set(re.findall(r"\b(vly_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libvalley_b200.so does not export {name}"
+    assert declared <= set(_lib.SIGNATURES), declared - set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.vly_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from valley_b200.model import ValleyConfig, ValleyLlamaForCausalLM
+    with pytest.raises(Exception) as ei:
+        ValleyLlamaForCausalLM(ValleyConfig.from_spec(syn.TINY), 0)
+    assert "no CUDA device" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def plan(ids, T, tokens):
+    lib = _lib.load()
+    ids = ids.to(torch.int64).contiguous()
+    B, S = ids.shape
+    smap, iidx = torch.empty(B, S, dtype=torch.int32), torch.empty(B, dtype=torch.int32)
+    code = lib.vly_build_splice_map(C.cast(ids.data_ptr(), C.POINTER(C.c_int64)), B, S, T, C.byref(tokens),
+                                    C.cast(smap.data_ptr(), C.POINTER(C.c_int32)), C.cast(iidx.data_ptr(), C.POINTER(C.c_int32)))
+    return code, smap, iidx
+
+
+def vly_tokens(spec, **over):
+    t = dict(syn.sentinel_ids(spec))
+    t.update(over)
+    return _lib.VlyTokens(t["im_patch_token"], t["im_start_token"], t["im_end_token"], t["vi_frame_token"], t["vi_start_token"], t["vi_end_token"])
+
+
+def oracle_map(ids_row, T, tok, H=8):
+    """Run the oracle's splice on marker embeddings to recover the source map it implies."""
+    S = ids_row.shape[0]
+    emb = torch.full((S, H), -1.0)
+    feat = torch.zeros(T, 257, H)
+    feat[:, 1:, :] = torch.arange(256, dtype=torch.float32)[None, :, None]        # mean over T keeps j
+    feat[:, 0, :] = (256 + torch.arange(T, dtype=torch.float32))[:, None]
+    out = O.splice_one(ids_row, emb, feat, tok)
+    return out[:, 0].round().to(torch.int32)
+
+
+@pytest.mark.parametrize("T", [1, 3, 8])
+def test_splice_plan_equals_oracle_on_golden_cases(T):
+    spec = syn.TINY
+    tok, t = Hh.oracle_tok(spec), syn.sentinel_ids(spec)
+    base = syn.make_prompt_ids(spec, 1, T, 0)[0]
+    mid = [t["im_start_token"]] + [t["im_patch_token"]] * 256 + [t["im_end_token"]]
+    cases = {
+        "plain_video": base,
+        "video_fallback_count": torch.where(torch.arange(base.numel()) == int((base == t["vi_frame_token"]).nonzero()[0]), torch.tensor(5), base),
+        "two_images": torch.cat([base, torch.tensor(mid), torch.tensor([9, 10])]),
+        "image_only": torch.cat([torch.tensor([1, 11, 12]), torch.tensor(mid), torch.tensor([13, 14, 15])]),
+        "vi_end_misplaced": torch.where(torch.arange(base.numel()) == int((base == t["vi_end_token"]).nonzero()[0]), torch.tensor(6), base),
+    }
+    for name, row in cases.items():
+        code, smap, iidx = plan(row[None], T, vly_tokens(spec))
+        assert code == 0, (name, _lib.load().vly_last_error())
+        assert iidx[0] == 0
+        assert torch.equal(smap[0], oracle_map(row, T, tok)), name
+
+
+def test_splice_plan_mixed_batch_and_unset_video_tokens():
+    spec = syn.TINY
+    T = 3
+    base = syn.make_prompt_ids(spec, 1, T, 0)[0]
+    plain = torch.randint(3, spec.vocab_size - 8, base.shape, generator=torch.Generator().manual_seed(5))
+    code, smap, iidx = plan(torch.stack([plain, base, plain, base]), T, vly_tokens(spec))
+    assert code == 0 and iidx.tolist() == [-1, 0, -1, 1]            # cur_image_idx advances only for multimodal rows
+    assert (smap[0] == -1).all() and (smap[2] == -1).all() and torch.equal(smap[1], smap[3])
+    # vi_* ids never set on vision_tower.config -> AttributeError in the reference -> image-only result
+    code, smap2, _ = plan(base[None], T, vly_tokens(spec, vi_frame_token=-1, vi_start_token=-1, vi_end_token=-1))
+    assert code == 0 and smap2.max() == 255 and (smap2 >= 0).sum() == 256
+
+
+def test_splice_plan_errors_match_reference_messages():
+    spec = syn.TINY
+    t = syn.sentinel_ids(spec)
+    base = syn.make_prompt_ids(spec, 1, 3, 0)[0]
+    lib = _lib.load()
+    unbalanced = base.clone()
+    unbalanced[(unbalanced == t["im_end_token"]).nonzero()[0]] = 7
+    code, _, _ = plan(unbalanced[None], 3, vly_tokens(spec))
+    assert code == _lib.VLY_ERR_IM_COUNT and lib.vly_last_error() == b"The number of im_start_token and im_end_token should be the same"
+    with pytest.raises(ValueError):
+        _lib.check(code)
+    cut = torch.cat([unbalanced, torch.tensor([t["im_end_token"]])])
+    code, _, _ = plan(cut[None], 3, vly_tokens(spec))
+    assert code == _lib.VLY_ERR_IM_CUT and lib.vly_last_error() == b"Seems that the image is cut."
+    short = base[: int((base == t["im_start_token"]).nonzero()[0]) + 100].clone()
+    short[-1] = t["im_end_token"]                                   # counts balanced, block runs past the row
+    code, _, _ = plan(short[None], 3, vly_tokens(spec))
+    assert code == _lib.VLY_ERR_INDEX
+    with pytest.raises(IndexError):
+        _lib.check(code)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_tiny.pt"))
+    for case, d in g["errors"].items():                              # the reference's own failing inputs
+        code, _, _ = plan(d["ids"], 3, vly_tokens(spec))
+        assert code < 0 and lib.vly_last_error().decode() == d["message"], case
+
+
+def test_empty_and_degenerate_inputs():
+    spec = syn.TINY
+    code, smap, iidx = plan(torch.zeros(0, 5, dtype=torch.int64), 3, vly_tokens(spec))
+    assert code == 0
+    code, smap, iidx = plan(torch.full((2, 4), 5, dtype=torch.int64), 0, vly_tokens(spec))
+    assert code == 0 and (smap == -1).all() and iidx.tolist() == [-1, -1]

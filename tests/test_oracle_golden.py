@@ -1,0 +1,52 @@
+"""CPU: the oracle must reproduce the REFERENCE's outputs stored in tests/golden/ (written by
+oracle/make_golden.py from the live reference classes).  fp32, tight tolerance."""
+import os
+
+import pytest
+import torch
+
+import helpers as Hh
+from oracle import valley_oracle as O
+from valley_b200 import synthetic as syn
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny-wide"])
+def test_oracle_matches_reference_fixture(name):
+    g = torch.load(os.path.join(GOLD, f"ref_{name}.pt"))
+    spec = syn.SPECS[name]
+    sd = syn.make_state_dict(spec, g["seed"])
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    ids, px = syn.make_prompt_ids(spec, g["B"], g["T"], g["seed"]), syn.make_pixels(g["B"], g["T"], g["seed"])
+    with torch.no_grad():
+        h2 = O.vit_hidden_state(sd, px[0], -2, num_layers=spec.vit_layers, heads=spec.vit_heads)
+        h1 = O.vit_hidden_state(sd, px[0], -1, num_layers=spec.vit_layers, heads=spec.vit_heads)
+        assert torch.allclose(h2[:, ::4, ::8], g["vit_hidden_m2_sub"], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(h1[:, ::4, ::8], g["vit_hidden_m1_sub"], rtol=1e-5, atol=1e-5)
+        logits = O.causal_lm_forward(sd, cfg, tok, ids, px, None)
+        assert torch.allclose(logits[:, -1], g["prefill_logits_last"], rtol=1e-4, atol=1e-5)
+        assert torch.allclose(logits[:, ::16, ::8], g["prefill_logits_sub"], rtol=1e-4, atol=1e-5)
+        n = g["greedy_tokens"].shape[1]
+        toks, logs = O.greedy_generate(sd, cfg, tok, ids, px, n, return_logits=True)
+        assert torch.equal(toks, g["greedy_tokens"])                       # token ids: exact
+        assert torch.allclose(logs, g["greedy_logits"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tiny"])
+def test_oracle_splice_cases_match_reference(name):
+    g = torch.load(os.path.join(GOLD, f"ref_{name}.pt"))
+    spec = syn.SPECS[name]
+    sd = syn.make_state_dict(spec, g["seed"])
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    px = syn.make_pixels(g["B"], g["T"], g["seed"])
+    with torch.no_grad():
+        for case, d in g["splice"].items():
+            cpx = px[:1, : d["n_frames"]]
+            feats = O.encode_images(sd, cpx, cfg.mm_vision_select_layer, num_layers=cfg.vit_layers)
+            emb = O.prepare_inputs_embeds(sd, d["ids"], feats, tok)
+            assert torch.allclose(emb[:, :, ::8], d["embeds_sub"], rtol=1e-5, atol=1e-6), case
+        for case, d in g["errors"].items():
+            with pytest.raises(ValueError) as ei:
+                O.causal_lm_forward(sd, cfg, tok, d["ids"], px[:1], None)
+            assert str(ei.value) == d["message"], case

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -17,6 +18,8 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "simt_kernels.cuh"
+#include "decode_kernels.cuh"
+#include "decode_mega.cuh"
 
 using namespace vly;
 typedef __nv_bfloat16 bf16;
@@ -129,12 +132,31 @@ struct vly_kv {
   long long* cur_tokens = nullptr;    // [B]
   long long* gen_tokens = nullptr;    // [B, Smax]
   int nsplit = 1, gemv_grid = 0;
+  PhaseDesc* d_phases = nullptr;
+  int n_phases = 0;
+  unsigned int* grid_counter = nullptr;
+  long long* dbg = nullptr;
   cudaGraphExec_t graph = nullptr;
   int graph_nodes = 0;
   size_t layer_stride() const { return (size_t)2 * B * ctx->cfg.num_attention_heads * Smax * 128; }
   bf16* k_layer(int l) const { return cache + (size_t)l * layer_stride(); }
   bf16* v_layer(int l) const { return k_layer(l) + layer_stride() / 2; }
 };
+
+// decode implementation: 2 = one persistent cooperative kernel per step (default), 1 = per-op TMA-ring kernels + PDL,
+// 0 = per-op register-streaming kernels (generation 1).  VLY_DECODE=v1|ring|mega overrides (A/B measurements).
+static int decode_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLY_DECODE");
+    v = 2;
+    if (e && !strcmp(e, "v1")) v = 0;
+    if (e && !strcmp(e, "ring")) v = 1;
+    if (getenv("VLY_DECODE_V1")) v = 0;
+  }
+  return v;
+}
+static bool use_decode_v1() { return decode_mode() == 0; }
 
 static inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
 
@@ -747,8 +769,12 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   CK(cudaMalloc((void**)&kv->cache, cache_elems * 2));
   CK(cudaMemset(kv->cache, 0, cache_elems * 2));   // padded keys must be finite: P(=0) * V(pad) must stay 0
   // split-KV factor: enough CTAs to cover the GPU about twice
-  int ns = (2 * c->num_sms + batch * nH - 1) / (batch * nH);
-  kv->nsplit = ns < 1 ? 1 : (ns > 16 ? 16 : ns);
+  if (decode_mode() == 0) {
+    int ns = (2 * c->num_sms + batch * nH - 1) / (batch * nH);
+    kv->nsplit = ns < 1 ? 1 : (ns > 16 ? 16 : ns);
+  } else {
+    kv->nsplit = kv->Smax / kDecSplitKeys;      // fixed 64-key splits; splits past the current length exit immediately
+  }
   kv->gemv_grid = 2 * c->num_sms;
   CK(cudaMalloc((void**)&kv->d_len, 8));
   kv->d_step = kv->d_len + 1;
@@ -759,13 +785,33 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   CK(cudaMalloc((void**)&kv->hb, (size_t)batch * I * 2));
   CK(cudaMalloc((void**)&kv->part_o, (size_t)batch * nH * kv->nsplit * 128 * 4));
   CK(cudaMalloc((void**)&kv->part_ml, (size_t)batch * nH * kv->nsplit * sizeof(float2)));
-  CK(cudaMalloc((void**)&kv->counters, ((size_t)batch * nH + 1) * 4));
-  CK(cudaMemset(kv->counters, 0, ((size_t)batch * nH + 1) * 4));
+  CK(cudaMalloc((void**)&kv->counters, ((size_t)batch * nH + 2) * 4));
+  CK(cudaMemset(kv->counters, 0, ((size_t)batch * nH + 2) * 4));
+  kv->grid_counter = kv->counters + (size_t)batch * nH + 1;
   CK(cudaMalloc((void**)&kv->part_val, (size_t)batch * kv->gemv_grid * 4));
   CK(cudaMalloc((void**)&kv->part_idx, (size_t)batch * kv->gemv_grid * 4));
   CK(cudaMalloc((void**)&kv->logits, (size_t)batch * V * 4));
   CK(cudaMalloc((void**)&kv->cur_tokens, (size_t)batch * 8));
   CK(cudaMalloc((void**)&kv->gen_tokens, (size_t)batch * kv->Smax * 8));
+  CK(cudaMalloc((void**)&kv->dbg, 1024 * 8 * 8));
+  {  // phase table of the persistent decode-step kernel: execution order of one step
+    std::vector<PhaseDesc> ph;
+    for (int l = 0; l < L; ++l) {
+      const LlamaLayerW& w = c->layers[l];
+      PhaseDesc d = {};
+      d.layer = l; d.kcache = kv->k_layer(l); d.vcache = kv->v_layer(l);
+      d.type = PH_QKV; d.N = 3 * H; d.K = H; d.W = w.wqkv; d.x_in = kv->x; d.out = kv->q; ph.push_back(d);
+      d.type = PH_ATTN; d.N = 0; d.K = 0; d.W = nullptr; d.x_in = nullptr; d.out = kv->attn; ph.push_back(d);
+      d.type = PH_OPROJ; d.N = H; d.K = H; d.W = w.wo; d.x_in = kv->attn; d.out = kv->x; ph.push_back(d);
+      d.type = PH_GATEUP; d.N = 2 * I; d.K = H; d.W = w.wgu; d.x_in = kv->x; d.out = kv->hb; ph.push_back(d);
+      d.type = PH_DOWN; d.N = H; d.K = I; d.W = w.wdown; d.x_in = kv->hb; d.out = kv->x; ph.push_back(d);
+    }
+    PhaseDesc d = {};
+    d.type = PH_LOGITS; d.N = V; d.K = H; d.W = c->lm_head; d.x_in = kv->x; d.out = nullptr; ph.push_back(d);
+    kv->n_phases = (int)ph.size();
+    CK(cudaMalloc((void**)&kv->d_phases, ph.size() * sizeof(PhaseDesc)));
+    CK(cudaMemcpy(kv->d_phases, ph.data(), ph.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice));
+  }
   *out = kv;
   return VLY_OK;
 }
@@ -774,7 +820,7 @@ extern "C" void vly_kv_destroy(vly_kv* kv) {
   if (!kv) return;
   cudaSetDevice(kv->ctx->cfg.device);
   if (kv->graph) cudaGraphExecDestroy(kv->graph);
-  void* ps[] = {kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
+  void* ps[] = {kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
   for (void* p : ps)
     if (p) cudaFree(p);
   delete kv;
@@ -836,6 +882,61 @@ static int launch_gemv(vly_ctx* c, GemvParams p, int grid, cudaStream_t st) {
   return VLY_OK;
 }
 
+// ---- generation-2 decode launchers (TMA ring + programmatic dependent launch) ----
+template <typename Kern, typename... Args>
+static cudaError_t launch_ex(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static const bool no_pdl = getenv("VLY_NO_PDL") != nullptr;
+  cfg.numAttrs = (pdl && !no_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+template <int MODE>
+static int launch_gemv_ring(vly_ctx* c, GemvParams p, bool pdl, cudaStream_t st) {
+  const int bmax = p.B <= 1 ? 1 : (p.B <= 2 ? 2 : 4);
+  if (p.B > 4) return fail(VLY_ERR_INVALID, "gemv: batch %d > 4 per call (callers split the batch)", p.B);
+  if (p.ldx == 0) p.ldx = p.K;
+  const size_t x_bytes = (((size_t)bmax * p.K * 2) + 15) & ~size_t(15);
+  const size_t misc = 4096 + 128;
+  int n_stages = (int)((113 * 1024 - (long long)x_bytes - (long long)misc) / RingCfg::STAGE_BYTES);   // two kernels co-resident per SM
+  if (n_stages >= 3) n_stages = n_stages > 6 ? 6 : n_stages;
+  else {
+    n_stages = (int)((225 * 1024 - (long long)x_bytes - (long long)misc) / RingCfg::STAGE_BYTES);
+    if (n_stages > RingCfg::MAX_STAGES) n_stages = RingCfg::MAX_STAGES;
+    if (n_stages < 1) return fail(VLY_ERR_INVALID, "gemv: activation rows (B=%d, K=%d) do not fit in shared memory", p.B, p.K);
+  }
+  const size_t smem = (size_t)n_stages * RingCfg::STAGE_BYTES + x_bytes + misc;
+  const int groups = (p.N + RingCfg::ROWS - 1) / RingCfg::ROWS;
+  const int grid = groups < c->num_sms ? groups : c->num_sms;
+  cudaError_t e;
+#define VLY_RING_CASE(BM)                                                                                                   \
+  {                                                                                                                         \
+    static size_t max_set = 0;                                                                                              \
+    if (smem > max_set) {                                                                                                   \
+      CK(cudaFuncSetAttribute(gemv_ring_kernel<BM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      /* keep the SM at its maximum shared-memory carve-out so the NEXT kernel's CTA can co-reside (PDL overlap) */      \
+      CK(cudaFuncSetAttribute(gemv_ring_kernel<BM, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));            \
+      max_set = smem;                                                                                                       \
+    }                                                                                                                       \
+    e = launch_ex(gemv_ring_kernel<BM, MODE>, dim3(grid), dim3(RingCfg::THREADS), smem, st, pdl, p, n_stages);              \
+  }
+  if (bmax == 1) VLY_RING_CASE(1)
+  else if (bmax == 2) VLY_RING_CASE(2)
+  else VLY_RING_CASE(4)
+#undef VLY_RING_CASE
+  c->launches++;
+  CK(e);
+  return VLY_OK;
+}
+
 // Enqueue one decode step for batch rows [b0, b0+nb) of kv (nb <= 4).  Reads kv->cur_tokens, writes kv->cur_tokens.
 static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump, cudaStream_t st) {
   const vly_config& g = c->cfg;
@@ -858,7 +959,8 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
       GemvParams p = {};
       p.N = 3 * H; p.K = H; p.B = nb; p.W = w.wqkv; p.x = x; p.eps = g.rms_norm_eps;
       p.out = q; p.rope = c->rope; p.seq_len = kv->d_len; p.H = H; p.nH = nH; p.Smax = kv->Smax; p.kcache = kc; p.vcache = vc;
-      TRY(launch_gemv<GEMV_QKV_ROPE>(c, p, kv->gemv_grid, st));
+      if (use_decode_v1()) TRY(launch_gemv<GEMV_QKV_ROPE>(c, p, kv->gemv_grid, st));
+      else TRY(launch_gemv_ring<GEMV_QKV_ROPE>(c, p, true, st));
     }
     {
       DecAttnParams p = {};
@@ -869,25 +971,38 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
       p.counters = kv->counters + (size_t)b0 * nH;
       p.out = attn;
       p.scale_log2e = 0.08838834764831845f * 1.4426950408889634f;
-      dim3 grid(nb * nH, kv->nsplit);
-      decode_attention_kernel<<<grid, 128, attn_smem, st>>>(p);
+      if (use_decode_v1()) {
+        dim3 grid(nb * nH, kv->nsplit);
+        decode_attention_kernel<<<grid, 128, attn_smem, st>>>(p);
+        CKL();
+      } else {
+        static bool v2_attr = false;
+        if (!v2_attr) {
+          CK(cudaFuncSetAttribute(decode_attention_v2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+          v2_attr = true;
+        }
+        dim3 grid(nb * nH, kv->nsplit);
+        CK(launch_ex(decode_attention_v2_kernel, grid, dim3(128), 0, st, true, p));
+      }
       c->launches++;
-      CKL();
     }
     {
       GemvParams p = {};
       p.N = H; p.K = H; p.B = nb; p.W = w.wo; p.x = attn; p.out = x; p.res = x;
-      TRY(launch_gemv<GEMV_RESIDUAL>(c, p, kv->gemv_grid, st));
+      if (use_decode_v1()) TRY(launch_gemv<GEMV_RESIDUAL>(c, p, kv->gemv_grid, st));
+      else TRY(launch_gemv_ring<GEMV_RESIDUAL>(c, p, true, st));
     }
     {
       GemvParams p = {};
       p.N = 2 * I; p.K = H; p.B = nb; p.W = w.wgu; p.x = x; p.eps = g.rms_norm_eps; p.out = hb;
-      TRY(launch_gemv<GEMV_SWIGLU>(c, p, kv->gemv_grid, st));
+      if (use_decode_v1()) TRY(launch_gemv<GEMV_SWIGLU>(c, p, kv->gemv_grid, st));
+      else TRY(launch_gemv_ring<GEMV_SWIGLU>(c, p, true, st));
     }
     {
       GemvParams p = {};
       p.N = H; p.K = I; p.B = nb; p.W = w.wdown; p.x = hb; p.out = x; p.res = x;
-      TRY(launch_gemv<GEMV_RESIDUAL>(c, p, kv->gemv_grid, st));
+      if (use_decode_v1()) TRY(launch_gemv<GEMV_RESIDUAL>(c, p, kv->gemv_grid, st));
+      else TRY(launch_gemv_ring<GEMV_RESIDUAL>(c, p, true, st));
     }
   }
   {
@@ -903,7 +1018,8 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
     p.step = kv->d_step;
     p.seq_len_rw = kv->d_len;
     p.bump = bump ? 1 : 0;   // only the last batch group of a step advances the step / length counters
-    TRY(launch_gemv<GEMV_LOGITS>(c, p, kv->gemv_grid, st));
+    if (use_decode_v1()) TRY(launch_gemv<GEMV_LOGITS>(c, p, kv->gemv_grid, st));
+    else TRY(launch_gemv_ring<GEMV_LOGITS>(c, p, true, st));
   }
   return VLY_OK;
 }
@@ -1005,7 +1121,8 @@ extern "C" int vly_llama_prefill(vly_ctx* c, vly_kv* kv, const void* inputs_embe
     p.next_tokens = kv->cur_tokens + b0;
     p.out_tokens = nullptr;
     p.step = kv->d_step; p.seq_len_rw = kv->d_len; p.bump = 0;
-    TRY(launch_gemv<GEMV_LOGITS>(c, p, kv->gemv_grid, st));
+    if (use_decode_v1()) TRY(launch_gemv<GEMV_LOGITS>(c, p, kv->gemv_grid, st));
+    else TRY(launch_gemv_ring<GEMV_LOGITS>(c, p, false, st));
   }
   if (logits_mode == 1) CK(cudaMemcpyAsync(logits_dev, kv->logits, (size_t)B * V * 4, cudaMemcpyDeviceToDevice, st));
   if (next_tokens_dev) CK(cudaMemcpyAsync(next_tokens_dev, kv->cur_tokens, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
@@ -1019,7 +1136,65 @@ extern "C" int vly_llama_prefill(vly_ctx* c, vly_kv* kv, const void* inputs_embe
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
+static long long* g_mega_dbg = nullptr;
+extern "C" int vly_debug_mega_counters(long long* host_out, int n) {
+  if (!g_mega_dbg) return -1;
+  return cudaMemcpy(host_out, g_mega_dbg, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
+  const vly_config& g = c->cfg;
+  const int B = kv->B, bmax = B <= 1 ? 1 : (B <= 2 ? 2 : 4);
+  StepParams p = {};
+  p.phases = kv->d_phases; p.n_phases = kv->n_phases;
+  p.B = B; p.H = g.hidden_size; p.nH = g.num_attention_heads; p.Smax = kv->Smax; p.V = g.vocab_size;
+  p.Kmax = g.intermediate_size > g.hidden_size ? g.intermediate_size : g.hidden_size;
+  p.eps = g.rms_norm_eps; p.scale_log2e = 0.08838834764831845f * 1.4426950408889634f;
+  p.rope = c->rope; p.seq_len = kv->d_len; p.step = kv->d_step; p.embed = c->embed; p.tokens_in = kv->cur_tokens;
+  p.x = kv->x; p.q = kv->q; p.attn = kv->attn;
+  p.part_o = kv->part_o; p.part_ml = kv->part_ml; p.attn_counters = kv->counters; p.nsplit = kv->nsplit;
+  p.logits = kv->logits; p.part_val = kv->part_val; p.part_idx = kv->part_idx;
+  p.next_tokens = kv->cur_tokens; p.out_tokens = kv->gen_tokens; p.out_stride = kv->Smax;
+  p.grid_counter = kv->grid_counter;
+  {
+    static const bool want = getenv("VLY_MEGA_DBG") != nullptr;
+    p.dbg = want ? kv->dbg : nullptr;
+    g_mega_dbg = kv->dbg;
+  }
+  const size_t x_bytes = (((size_t)bmax * p.Kmax * 2) + 127) & ~size_t(127);
+  const size_t misc = MegaCfg::ATTN_SCRATCH + 2 * MegaCfg::MAX_STAGES * 8 + 2 * 16 * 4 * bmax * 4 + 64 * bmax + 512;
+  int n_stages = (int)((226 * 1024 - (long long)x_bytes - (long long)misc) / MegaCfg::STAGE_BYTES);
+  if (n_stages > MegaCfg::MAX_STAGES) n_stages = MegaCfg::MAX_STAGES;
+  {
+    // measured on B200 (tools/membw.cu): ~96 KB of bulk copies in flight per SM streams at 7.2-7.5 TB/s, 192 KB at 5.2-6 TB/s
+    static const int want = getenv("VLY_MEGA_STAGES") ? atoi(getenv("VLY_MEGA_STAGES")) : 3;
+    if (n_stages > want) n_stages = want;
+  }
+  if (n_stages < 2) return fail(VLY_ERR_INVALID, "decode: activations (B=%d, K=%d) leave no room for the weight ring", B, p.Kmax);
+  p.n_stages = n_stages;
+  const size_t smem = (size_t)n_stages * MegaCfg::STAGE_BYTES + x_bytes + misc;
+  CK(cudaMemsetAsync(kv->grid_counter, 0, 4, st));
+  void* args[] = {&p};
+  cudaError_t e;
+#define VLY_MEGA_CASE(BM)                                                                                               \
+  {                                                                                                                     \
+    static size_t max_set = 0;                                                                                          \
+    if (smem > max_set) {                                                                                               \
+      CK(cudaFuncSetAttribute(decode_step_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      max_set = smem;                                                                                                   \
+    }                                                                                                                   \
+    e = cudaLaunchCooperativeKernel((void*)decode_step_kernel<BM>, dim3(c->num_sms), dim3(MegaCfg::THREADS), args, smem, st); \
+  }
+  if (bmax == 1) VLY_MEGA_CASE(1)
+  else if (bmax == 2) VLY_MEGA_CASE(2)
+  else VLY_MEGA_CASE(4)
+#undef VLY_MEGA_CASE
+  c->launches++;
+  CK(e);
+  return VLY_OK;
+}
+
 static int enqueue_full_step(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
+  if (decode_mode() == 2 && kv->B <= 4) return launch_decode_mega(c, kv, st);
   for (int b0 = 0; b0 < kv->B; b0 += 4) {
     const int nb = (kv->B - b0) < 4 ? (kv->B - b0) : 4;
     TRY(enqueue_decode_step(c, kv, b0, nb, b0 + 4 >= kv->B, st));

@@ -93,6 +93,17 @@ VLY_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): size multiple of 16 B, both addresses 16 B aligned.
+VLY_DEVINL void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Programmatic dependent launch: wait = all memory of the prerequisite grids is visible; launch_dependents = the
+// next grid in the stream may start being scheduled (it still blocks in ITS wait until this grid has completed).
+VLY_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+VLY_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, commit, mma, ld
 // ------------------------------------------------------------------------------------------

@@ -59,12 +59,14 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;                        // 2 accumulator stages (256 or 512)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int VEC_BYTES = 2 /*acc stages*/ * 2 /*bias, colsum*/ * BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + VEC_BYTES;
   static constexpr int THREADS = 192;
 };
 
-VLY_DEVINL float quick_gelu_f(float v) { return v * __frcp_rn(1.0f + __expf(-1.702f * v)); }
-VLY_DEVINL float silu_f(float v) { return v * __frcp_rn(1.0f + __expf(-v)); }
+// x*sigmoid(1.702x) and x*sigmoid(x) on the fast MUFU path (ex2.approx + rcp.approx)
+VLY_DEVINL float quick_gelu_f(float v) { return __fdividef(v, 1.0f + fast_exp2(-2.4554669595930156f * v)); }
+VLY_DEVINL float silu_f(float v) { return __fdividef(v, 1.0f + fast_exp2(-1.4426950408889634f * v)); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
@@ -82,6 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* svec = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);   // [2][2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -163,6 +166,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int row = m_blk * BM + r_in_tile;
       const bool row_ok = row < p.M;
 
+      // per-column vectors of this tile -> smem once (instead of per-element global loads in every thread)
+      constexpr bool kHasVec = (EPI == EPI_BIAS || EPI == EPI_BIAS_RES_STATS || EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU);
+      float* sbias = svec + as * 2 * BN;
+      float* scol = sbias + BN;
+      if constexpr (kHasVec) {
+        const int e = threadIdx.x - 64;
+        for (int i = e; i < BN; i += 128) {
+          const int n = n_blk * BN + i;
+          sbias[i] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
+          if constexpr (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU) scol[i] = (n < p.N) ? __ldg(p.colsum + n) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      // residual rows do not depend on the MMA: issue every load of the tile before waiting for the accumulator
+      uint4 resv[(EPI == EPI_BIAS_RES_STATS) ? BN / 8 : 1];
+      if constexpr (EPI == EPI_BIAS_RES_STATS) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n_blk * BN);
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j)
+          resv[j] = (row_ok && n_blk * BN + j * 8 < p.N) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+      }
+
       float mean = 0.f, rstd = 1.f;
       if constexpr (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU || EPI == EPI_RMS_QKV_ROPE || EPI == EPI_RMS_SWIGLU ||
                     EPI == EPI_RMS_F32) {
@@ -195,7 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       float st_sum = 0.f, st_sq = 0.f;
-#pragma unroll 1
+      constexpr int kChunkUnroll = (EPI == EPI_BIAS_RES_STATS) ? BN / 32 : 1;   // keeps resv[] in registers
+#pragma unroll kChunkUnroll
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         __syncwarp();
@@ -208,18 +234,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 
         if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_RES_STATS) {
-          if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
           }
         }
         if constexpr (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU) {
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
+          const float4* c4 = reinterpret_cast<const float4*>(scol + c * 32);
+          const float nm = -mean * rstd;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float cs = __ldg(p.colsum + n0 + i), bb = __ldg(p.bias + n0 + i);
-            float t = rstd * (v[i] - mean * cs) + bb;
-            if constexpr (EPI == EPI_LN_BIAS_GELU) t = quick_gelu_f(t);
-            v[i] = t;
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j], cc = c4[j];
+            const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, cq[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+              float t = fmaf(rstd, v[4 * j + t4], fmaf(nm, cq[t4], bq[t4]));   // rstd*(acc - mean*colsum) + bias
+              if constexpr (EPI == EPI_LN_BIAS_GELU) t = quick_gelu_f(t);
+              v[4 * j + t4] = t;
+            }
           }
         }
         if constexpr (EPI == EPI_RMS_QKV_ROPE || EPI == EPI_RMS_SWIGLU || EPI == EPI_RMS_F32) {
@@ -229,11 +264,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
         if constexpr (EPI == EPI_BIAS_RES_STATS) {
           // residual add, bf16 rounding, partial row statistics of the ROUNDED values
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0);
           uint4 o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 rr = __ldg(rp + j);
+            const uint4 rr = resv[c * 4 + j];
             const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
             uint32_t ow[4];
 #pragma unroll

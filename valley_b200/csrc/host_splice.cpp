@@ -15,7 +15,8 @@
 extern "C" int vly_build_splice_map(const int64_t* ids, int B, int S, int T, const vly_tokens* tok, int32_t* src_map,
                                      int32_t* img_idx) {
   extern void vly_set_error_(const char*);
-  if (ids == nullptr || tok == nullptr || src_map == nullptr || img_idx == nullptr || B < 0 || S < 0 || T < 0) {
+  if (B == 0) return VLY_OK;   // empty batch: nothing to plan
+  if (tok == nullptr || img_idx == nullptr || B < 0 || S < 0 || T < 0 || (S > 0 && (ids == nullptr || src_map == nullptr))) {
     vly_set_error_("vly_build_splice_map: null argument or negative size");
     return VLY_ERR_INVALID;
   }

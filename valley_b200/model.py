@@ -202,6 +202,8 @@ class ValleyLlamaForCausalLM:
         self.model = ValleyLlamaModel(self)
         self.training = False
         self.logits_all_positions = True      # reference behaviour (valley_model.py:304-305); generate() uses last-only
+        import threading
+        self._cache_pool, self._pool_lock = {}, threading.Lock()
 
     # ---------------- lifetime / weights ----------------
     def __del__(self):
@@ -364,6 +366,25 @@ class ValleyLlamaForCausalLM:
     def new_cache(self, batch: int, max_seq: Optional[int] = None) -> ValleyKVCache:
         return ValleyKVCache(self, batch, max_seq or self.config.max_position_embeddings)
 
+    def _borrow_cache(self, batch: int) -> ValleyKVCache:
+        """generate() recycles its KV caches (and the CUDA graph captured on them) instead of paying a
+        multi-GB cudaMalloc + graph capture per request.  The pool is per model instance and lock-protected
+        (model_worker.py:467-474 calls the model from several threads)."""
+        with self._pool_lock:
+            lst = self._cache_pool.setdefault(batch, [])
+            c = lst.pop() if lst else None
+        if c is None:
+            c = self.new_cache(batch)
+        else:
+            c.reset()
+        return c
+
+    def _return_cache(self, c: ValleyKVCache):
+        with self._pool_lock:
+            lst = self._cache_pool.setdefault(c.batch, [])
+            if len(lst) < 2:
+                lst.append(c)
+
     def _prefill(self, cache: ValleyKVCache, embeds: torch.Tensor, logits_mode: int):
         B, S, _ = embeds.shape
         V = self.config.vocab_size
@@ -445,8 +466,15 @@ class ValleyLlamaForCausalLM:
         n_new = max(0, min(max_new_tokens, room))
         if n_new == 0:
             return input_ids.to(self.device)
-        cache = self.new_cache(B)
         _, _, _, embeds, _ = self.prepare_inputs_labels_for_multimodal(input_ids, None, None, None, images)
+        cache = self._borrow_cache(B)
+        try:
+            return self._generate_with_cache(cache, input_ids, embeds, n_new, do_sample, temperature, stopping_criteria, eos_token_id)
+        finally:
+            self._return_cache(cache)
+
+    def _generate_with_cache(self, cache, input_ids, embeds, n_new, do_sample, temperature, stopping_criteria, eos_token_id):
+        B = input_ids.shape[0]
         greedy = (not do_sample) or temperature < 1e-4
         logits, nxt = self._prefill(cache, embeds, 0 if greedy else 1)
         ids_dev = input_ids.to(self.device, torch.int64)
