@@ -297,8 +297,9 @@ def main():
 
     def prefill_only():
         _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, None)
+        cache = model.new_cache(vhi - vlo)
         def f():
-            cache = model.new_cache(vhi - vlo)
+            cache.reset()
             model._prefill(cache, emb, 0)
         return timed(f, 3, 2)[0]
     ms_prefill = prefill_only()

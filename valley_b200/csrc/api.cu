@@ -1161,7 +1161,7 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
     g_mega_dbg = kv->dbg;
   }
   const size_t x_bytes = (((size_t)bmax * p.Kmax * 2) + 127) & ~size_t(127);
-  const size_t misc = MegaCfg::ATTN_SCRATCH + 2 * MegaCfg::MAX_STAGES * 8 + 2 * 16 * 4 * bmax * 4 + 64 * bmax + 512;
+  const size_t misc = MegaCfg::ATTN_SCRATCH + (2 * MegaCfg::MAX_STAGES + 2 * MegaCfg::RED_SLOTS) * 8 + MegaCfg::RED_SLOTS * 16 * 4 * bmax * 4 + 128 * bmax + 512;
   int n_stages = (int)((226 * 1024 - (long long)x_bytes - (long long)misc) / MegaCfg::STAGE_BYTES);
   if (n_stages > MegaCfg::MAX_STAGES) n_stages = MegaCfg::MAX_STAGES;
   {
@@ -1228,11 +1228,15 @@ extern "C" int vly_generate_greedy(vly_ctx* c, vly_kv* kv, const int64_t* first_
   if (kv->host_len + n_steps > kv->Smax) return fail(VLY_ERR_INVALID, "vly_generate_greedy: %d cached + %d steps exceed the cache capacity %d", kv->host_len, n_steps, kv->Smax);
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  TRY(build_graph(c, kv));
+  static const bool no_graph = getenv("VLY_NO_GRAPH") != nullptr;   // profiling aid: eager launches instead of graph replay
+  if (!no_graph) TRY(build_graph(c, kv));
   CK(cudaMemcpyAsync(kv->cur_tokens, first_tokens, (size_t)kv->B * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(kv->d_step, 0, 4, st));
-  for (int i = 0; i < n_steps; ++i) CK(cudaGraphLaunch(kv->graph, st));
-  c->launches += (int64_t)n_steps * kv->graph_nodes;
+  for (int i = 0; i < n_steps; ++i) {
+    if (no_graph) TRY(enqueue_full_step(c, kv, st));
+    else CK(cudaGraphLaunch(kv->graph, st));
+  }
+  if (!no_graph) c->launches += (int64_t)n_steps * kv->graph_nodes;
   if (out_tokens)
     CK(cudaMemcpy2DAsync(out_tokens, (size_t)n_steps * 8, kv->gen_tokens, (size_t)kv->Smax * 8, (size_t)n_steps * 8, kv->B,
                          cudaMemcpyDeviceToDevice, st));

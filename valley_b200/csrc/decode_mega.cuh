@@ -8,10 +8,13 @@
 //                       (TMA) copies: 4 rows x 4096 columns = 32 KB per stage, mbarrier complete_tx.  It never waits for a
 //                       phase boundary -- weights do not depend on activations -- so while the consumers sit in a grid
 //                       barrier the ring fills with the NEXT phase's weights and HBM keeps streaming.
-//   warps 1..16       : consumers -- per phase: stage the activation rows in shared memory (RMSNorm statistics where a
-//                       norm is folded), multiply the ring stages (fp32 accumulate), reduce, fused epilogue (RoPE + KV
-//                       append, SwiGLU, residual, logits + arg-max).  The attention phase runs on four 128-thread teams
+//   warps 1..16       : compute -- per phase: stage the activation rows in shared memory (RMSNorm statistics where a
+//                       norm is folded), multiply the ring stages (fp32 accumulate), warp-reduce, and hand the 16 per-warp
+//                       partials of a 4-row unit to the finalize warp through a 4-slot mbarrier handoff -- there is NO
+//                       blocking barrier inside the streaming loop.  The attention phase runs on four 128-thread teams
 //                       (split-KV, last-arriver merge).  Phases are separated by a grid-wide barrier.
+//   warp 17           : finalize -- sums the partials and runs the fused epilogue (RoPE + KV append, SwiGLU, residual,
+//                       logits + running arg-max); its global operands are prefetched while the unit is being computed.
 // Cross-CTA activations are read with ld.global.cg (L2) -- the L1 of an SM is not coherent with other SMs' writes.
 #pragma once
 #include "common.cuh"
@@ -62,7 +65,8 @@ struct StepParams {
 struct MegaCfg {
   static constexpr int ROWS = 4, KC = 4096;
   static constexpr int STAGE_BYTES = ROWS * KC * 2;   // 32 KB
-  static constexpr int CONSUMERS = 512, THREADS = 544;
+  static constexpr int CONSUMERS = 512, THREADS = 576;   // producer warp + 16 compute warps + 1 finalize warp
+  static constexpr int RED_SLOTS = 4;
   static constexpr int MAX_STAGES = 6;
   static constexpr int ATTN_SCRATCH = 4 * (64 + 8 * 128 + 8) * 4;   // per team: scores[64] + redg[8][128] + wr
 };
@@ -85,18 +89,17 @@ VLY_DEVINL uint32_t ld_acquire_u32(const unsigned int* p) {
 
 // consumers-only grid barrier (512 threads per CTA take part; the producer warp streams on)
 VLY_DEVINL void grid_sync_consumers(unsigned int* counter, unsigned int target, int ct) {
-  asm volatile("bar.sync 2, 512;" ::: "memory");
+  asm volatile("bar.sync 2, 544;" ::: "memory");          // every write of this CTA happens-before thread 0's release
   if (ct == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (ld_acquire_u32(counter) < target) { __nanosleep(32); }
-    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+    while (ld_acquire_u32(counter) < target) {
+    }
   }
-  asm volatile("bar.sync 2, 512;" ::: "memory");
+  asm volatile("bar.sync 2, 544;" ::: "memory");
 }
 
 template <int BMAX>
-__global__ void __launch_bounds__(544, 1) decode_step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p) {
   using M = MegaCfg;
   constexpr int NV = M::ROWS * BMAX;
   extern __shared__ uint8_t msm_raw[];
@@ -107,8 +110,10 @@ __global__ void __launch_bounds__(544, 1) decode_step_kernel(const StepParams p)
   float* scratch = reinterpret_cast<float*>(tail);                                       // attention teams
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail + M::ATTN_SCRATCH);
   uint64_t* empty_bar = full_bar + M::MAX_STAGES;
-  float* red = reinterpret_cast<float*>(empty_bar + M::MAX_STAGES);                      // [2][16][NV]
-  float* rstd_s = red + 2 * 16 * NV;                                                     // [BMAX]
+  uint64_t* red_full = empty_bar + M::MAX_STAGES;                                        // [RED_SLOTS]
+  uint64_t* red_empty = red_full + M::RED_SLOTS;                                         // [RED_SLOTS]
+  float* red = reinterpret_cast<float*>(red_empty + M::RED_SLOTS);                       // [RED_SLOTS][16][NV]
+  float* rstd_s = red + M::RED_SLOTS * 16 * NV;                                          // [BMAX]
   float* bestv = rstd_s + BMAX;                                                          // [BMAX]
   int* besti = reinterpret_cast<int*>(bestv + BMAX);                                     // [BMAX]
   float* wred = reinterpret_cast<float*>(besti + BMAX);                                  // [16][BMAX]
@@ -119,6 +124,10 @@ __global__ void __launch_bounds__(544, 1) decode_step_kernel(const StepParams p)
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 16);
+    }
+    for (int i = 0; i < M::RED_SLOTS; ++i) {
+      mbar_init(&red_full[i], 16);
+      mbar_init(&red_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -152,123 +161,129 @@ __global__ void __launch_bounds__(544, 1) decode_step_kernel(const StepParams p)
     return;
   }
 
-  // ========================================= consumers =========================================
-  const int ct = tid - 32;            // 0..511
-  const int cw = warp - 1;            // 0..15
+  // ================================ compute warps (1..16) and finalize warp (17) ================================
+  const bool is_fin = (warp == 17);
+  const int ct = tid - 32;            // compute thread 0..511 (finalize warp: 512..543)
+  const int cw = warp - 1;            // compute warp 0..15
   const int pos = *p.seq_len;
   unsigned int sync_no = 0;
-  long long t_sync = 0, t_stage = 0, t_loop = 0, t_attn = 0, t_wait = 0, t0 = clock64();
+  long long t_sync = 0, t_stage = 0, t_loop = 0, t_attn = 0, t0 = clock64();
   // ---- phase -1: x = embed[token] (decode input) ----
   {
-    const int chunks = p.B * (p.H >> 3);
-    for (int i = blockIdx.x * M::CONSUMERS + ct; i < chunks; i += gridDim.x * M::CONSUMERS) {
-      const int b = i / (p.H >> 3), c = i % (p.H >> 3);
-      long long id = p.tokens_in[b];
-      id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
-      *reinterpret_cast<uint4*>(p.x + (size_t)b * p.H + c * 8) = *reinterpret_cast<const uint4*>(p.embed + (size_t)id * p.H + c * 8);
-    }
-    if (ct < BMAX) {
-      bestv[ct] = -INFINITY;
-      besti[ct] = 0;
+    if (!is_fin) {
+      const int chunks = p.B * (p.H >> 3);
+      for (int i = blockIdx.x * M::CONSUMERS + ct; i < chunks; i += gridDim.x * M::CONSUMERS) {
+        const int b = i / (p.H >> 3), c = i % (p.H >> 3);
+        long long id = p.tokens_in[b];
+        id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+        *reinterpret_cast<uint4*>(p.x + (size_t)b * p.H + c * 8) = *reinterpret_cast<const uint4*>(p.embed + (size_t)id * p.H + c * 8);
+      }
+    } else if (lane < BMAX) {
+      bestv[lane] = -INFINITY;
+      besti[lane] = 0;
     }
     grid_sync_consumers(p.grid_counter, (++sync_no) * gridDim.x, ct);
     t_sync += clock64() - t0;
   }
 
-  int st = 0, par = 0;
+  int st = 0;
   uint32_t ph = 0;
+  unsigned int unit_no = 0;           // running work-unit counter of this CTA: selects the handoff slot
   for (int pi = 0; pi < p.n_phases; ++pi) {
     const PhaseDesc d = p.phases[pi];
     t0 = clock64();
     if (d.type == PH_ATTN) {
-      // ------------------------------ attention: 4 teams of 128 threads ------------------------------
-      const int tm = cw >> 2, tt = ct & 127, tw = cw & 3;
-      float* sc = scratch + tm * (64 + 8 * 128 + 8);
-      float* redg = sc + 64;
-      const int len = pos + 1;
-      const int n_act = (len + 63) >> 6;
-      const int items = p.B * p.nH * n_act;
-      const int hl = lane & 15;
-      for (int it = blockIdx.x * 4 + tm; it < items; it += gridDim.x * 4) {
-        const int split = it % n_act, bh = it / n_act;
-        const int b = bh / p.nH, h = bh % p.nH;
-        const int k0 = split * 64, nk = min(len, k0 + 64) - k0;
-        const __nv_bfloat16* kb = d.kcache + ((size_t)bh * p.Smax) * 128;
-        const __nv_bfloat16* vb = d.vcache + ((size_t)bh * p.Smax) * 128;
-        float qf[8];
-        {
-          const uint4 w = ldcg_v4(p.q + (size_t)b * p.H + h * 128 + hl * 8);
-          qf[0] = bf16_lo(w.x); qf[1] = bf16_hi(w.x); qf[2] = bf16_lo(w.y); qf[3] = bf16_hi(w.y);
-          qf[4] = bf16_lo(w.z); qf[5] = bf16_hi(w.z); qf[6] = bf16_lo(w.w); qf[7] = bf16_hi(w.w);
-        }
-        for (int i0 = tw * 2; i0 < nk; i0 += 8) {
-          const int i = i0 + (lane >> 4);
-          const bool ok = i < nk;
-          uint4 w = make_uint4(0, 0, 0, 0);
-          if (ok) w = ldcg_v4(kb + (size_t)(k0 + i) * 128 + hl * 8);
-          float dd = qf[0] * bf16_lo(w.x) + qf[1] * bf16_hi(w.x) + qf[2] * bf16_lo(w.y) + qf[3] * bf16_hi(w.y) +
-                     qf[4] * bf16_lo(w.z) + qf[5] * bf16_hi(w.z) + qf[6] * bf16_lo(w.w) + qf[7] * bf16_hi(w.w);
-          dd += __shfl_xor_sync(0xffffffffu, dd, 8);
-          dd += __shfl_xor_sync(0xffffffffu, dd, 4);
-          dd += __shfl_xor_sync(0xffffffffu, dd, 2);
-          dd += __shfl_xor_sync(0xffffffffu, dd, 1);
-          if (ok && hl == 0) sc[i] = dd * p.scale_log2e;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-        const float s0 = lane < nk ? sc[lane] : -INFINITY, s1 = lane + 32 < nk ? sc[lane + 32] : -INFINITY;
-        const float m = warp_max(fmaxf(s0, s1));
-        const float e0 = lane < nk ? fast_exp2(s0 - m) : 0.f, e1 = lane + 32 < nk ? fast_exp2(s1 - m) : 0.f;
-        const float l = warp_sum(e0 + e1);
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-        if (tw == 0) {
-          if (lane < nk) sc[lane] = e0;
-          if (lane + 32 < nk) sc[lane + 32] = e1;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-        {
-          const int g = tt >> 4, dl = tt & 15;
-          float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          for (int i = g; i < nk; i += 8) {
-            const float pw = sc[i];
-            const uint4 w = ldcg_v4(vb + (size_t)(k0 + i) * 128 + dl * 8);
-            o[0] = fmaf(pw, bf16_lo(w.x), o[0]); o[1] = fmaf(pw, bf16_hi(w.x), o[1]);
-            o[2] = fmaf(pw, bf16_lo(w.y), o[2]); o[3] = fmaf(pw, bf16_hi(w.y), o[3]);
-            o[4] = fmaf(pw, bf16_lo(w.z), o[4]); o[5] = fmaf(pw, bf16_hi(w.z), o[5]);
-            o[6] = fmaf(pw, bf16_lo(w.w), o[6]); o[7] = fmaf(pw, bf16_hi(w.w), o[7]);
+      if (!is_fin) {
+        // ------------------------------ attention: 4 teams of 128 threads ------------------------------
+        const int tm = cw >> 2, tt = ct & 127, tw = cw & 3;
+        float* sc = scratch + tm * (64 + 8 * 128 + 8);
+        float* redg = sc + 64;
+        const int len = pos + 1;
+        const int n_act = (len + 63) >> 6;
+        const int items = p.B * p.nH * n_act;
+        const int hl = lane & 15;
+        for (int it = blockIdx.x * 4 + tm; it < items; it += gridDim.x * 4) {
+          const int split = it % n_act, bh = it / n_act;
+          const int b = bh / p.nH, h = bh % p.nH;
+          const int k0 = split * 64, nk = min(len, k0 + 64) - k0;
+          const __nv_bfloat16* kb = d.kcache + ((size_t)bh * p.Smax) * 128;
+          const __nv_bfloat16* vb = d.vcache + ((size_t)bh * p.Smax) * 128;
+          float qf[8];
+          {
+            const uint4 w = ldcg_v4(p.q + (size_t)b * p.H + h * 128 + hl * 8);
+            qf[0] = bf16_lo(w.x); qf[1] = bf16_hi(w.x); qf[2] = bf16_lo(w.y); qf[3] = bf16_hi(w.y);
+            qf[4] = bf16_lo(w.z); qf[5] = bf16_hi(w.z); qf[6] = bf16_lo(w.w); qf[7] = bf16_hi(w.w);
           }
+          for (int i0 = tw * 2; i0 < nk; i0 += 8) {
+            const int i = i0 + (lane >> 4);
+            const bool ok = i < nk;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (ok) w = ldcg_v4(kb + (size_t)(k0 + i) * 128 + hl * 8);
+            float dd = qf[0] * bf16_lo(w.x) + qf[1] * bf16_hi(w.x) + qf[2] * bf16_lo(w.y) + qf[3] * bf16_hi(w.y) +
+                       qf[4] * bf16_lo(w.z) + qf[5] * bf16_hi(w.z) + qf[6] * bf16_lo(w.w) + qf[7] * bf16_hi(w.w);
+            dd += __shfl_xor_sync(0xffffffffu, dd, 8);
+            dd += __shfl_xor_sync(0xffffffffu, dd, 4);
+            dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+            dd += __shfl_xor_sync(0xffffffffu, dd, 1);
+            if (ok && hl == 0) sc[i] = dd * p.scale_log2e;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
+          const float s0 = lane < nk ? sc[lane] : -INFINITY, s1 = lane + 32 < nk ? sc[lane + 32] : -INFINITY;
+          const float mx = warp_max(fmaxf(s0, s1));
+          const float e0 = lane < nk ? fast_exp2(s0 - mx) : 0.f, e1 = lane + 32 < nk ? fast_exp2(s1 - mx) : 0.f;
+          const float l = warp_sum(e0 + e1);
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
+          if (tw == 0) {
+            if (lane < nk) sc[lane] = e0;
+            if (lane + 32 < nk) sc[lane + 32] = e1;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
+          {
+            const int g = tt >> 4, dl = tt & 15;
+            float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = g; i < nk; i += 8) {
+              const float pw = sc[i];
+              const uint4 w = ldcg_v4(vb + (size_t)(k0 + i) * 128 + dl * 8);
+              o[0] = fmaf(pw, bf16_lo(w.x), o[0]); o[1] = fmaf(pw, bf16_hi(w.x), o[1]);
+              o[2] = fmaf(pw, bf16_lo(w.y), o[2]); o[3] = fmaf(pw, bf16_hi(w.y), o[3]);
+              o[4] = fmaf(pw, bf16_lo(w.z), o[4]); o[5] = fmaf(pw, bf16_hi(w.z), o[5]);
+              o[6] = fmaf(pw, bf16_lo(w.w), o[6]); o[7] = fmaf(pw, bf16_hi(w.w), o[7]);
+            }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) redg[g * 128 + dl * 8 + e] = o[e];
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-        float ot = 0.f;
+            for (int e = 0; e < 8; ++e) redg[g * 128 + dl * 8 + e] = o[e];
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
+          float ot = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) ot += redg[g * 128 + tt];
-        p.part_o[((size_t)bh * p.nsplit + split) * 128 + tt] = ot;
-        if (tt == 0) p.part_ml[(size_t)bh * p.nsplit + split] = make_float2(m, l);
-        __threadfence();
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-        if (tt == 0) team_flag[tm] = (atomicAdd(p.attn_counters + bh, 1u) == (unsigned)n_act - 1);
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-        if (team_flag[tm]) {
+          for (int g = 0; g < 8; ++g) ot += redg[g * 128 + tt];
+          p.part_o[((size_t)bh * p.nsplit + split) * 128 + tt] = ot;
+          if (tt == 0) p.part_ml[(size_t)bh * p.nsplit + split] = make_float2(mx, l);
           __threadfence();
-          float Mx = -INFINITY;
-          for (int s = 0; s < n_act; ++s) Mx = fmaxf(Mx, __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x));
-          float L = 0.f, acc = 0.f;
-          for (int s = 0; s < n_act; ++s) {
-            const float ms = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x), ls = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].y);
-            const float w = fast_exp2(ms - Mx);
-            L += ls * w;
-            acc += __ldcg(p.part_o + ((size_t)bh * p.nsplit + s) * 128 + tt) * w;
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
+          if (tt == 0) team_flag[tm] = (atomicAdd(p.attn_counters + bh, 1u) == (unsigned)n_act - 1);
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
+          if (team_flag[tm]) {
+            __threadfence();
+            float Mx = -INFINITY;
+            for (int s = 0; s < n_act; ++s) Mx = fmaxf(Mx, __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x));
+            float L = 0.f, acc = 0.f;
+            for (int s = 0; s < n_act; ++s) {
+              const float ms = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x), ls = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].y);
+              const float w = fast_exp2(ms - Mx);
+              L += ls * w;
+              acc += __ldcg(p.part_o + ((size_t)bh * p.nsplit + s) * 128 + tt) * w;
+            }
+            p.attn[(size_t)b * p.H + h * 128 + tt] = __float2bfloat16_rn(acc / L);
+            if (tt == 0) p.attn_counters[bh] = 0;
           }
-          p.attn[(size_t)b * p.H + h * 128 + tt] = __float2bfloat16_rn(acc / L);
-          if (tt == 0) p.attn_counters[bh] = 0;
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");   // scratch reuse by the next item
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");   // scratch reuse by the next item
       }
+      t_attn += clock64() - t0;
     } else {
       // ------------------------------ weight phase ------------------------------
       const bool norm = (d.type == PH_QKV || d.type == PH_GATEUP || d.type == PH_LOGITS);
-      {
+      if (!is_fin) {
         float sq[BMAX];
 #pragma unroll
         for (int b = 0; b < BMAX; ++b) sq[b] = 0.f;
@@ -294,130 +309,150 @@ __global__ void __launch_bounds__(544, 1) decode_step_kernel(const StepParams p)
             if (lane == 0) wred[cw * BMAX + b] = v;
           }
         }
-        asm volatile("bar.sync 2, 512;" ::: "memory");
-        if (norm && ct < BMAX) {
-          float t = 0.f;
-          for (int w = 0; w < 16; ++w) t += wred[w * BMAX + ct];
-          rstd_s[ct] = rsqrtf(t / d.K + p.eps);
-        }
-        asm volatile("bar.sync 2, 512;" ::: "memory");
       }
-      const int n_groups = (d.N + M::ROWS - 1) / M::ROWS;
-      const int n_slices = (d.K + M::KC - 1) / M::KC;
+      asm volatile("bar.sync 2, 544;" ::: "memory");
+      if (norm && !is_fin && ct < BMAX) {
+        float t = 0.f;
+        for (int w = 0; w < 16; ++w) t += wred[w * BMAX + ct];
+        rstd_s[ct] = rsqrtf(t / d.K + p.eps);
+      }
+      asm volatile("bar.sync 2, 544;" ::: "memory");
       t_stage += clock64() - t0;
       t0 = clock64();
-      for (int g = blockIdx.x; g < n_groups; g += gridDim.x, par ^= 1) {
-        const int n0 = g * M::ROWS;
-        const int rows = min(M::ROWS, d.N - n0);
-        float acc[NV];
+      const int n_groups = (d.N + M::ROWS - 1) / M::ROWS;
+      const int n_slices = (d.K + M::KC - 1) / M::KC;
+      if (!is_fin) {
+        // ===== compute warps: ring stage x activation rows -> per-warp partials -> handoff slot =====
+        for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
+          const int n0 = g * M::ROWS;
+          const int rows = min(M::ROWS, d.N - n0);
+          float acc[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-        for (int s = 0; s < n_slices; ++s) {
-          const int kc = min(M::KC, d.K - s * M::KC);
-          {
-            const long long tw0 = clock64();
+          for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+          for (int s = 0; s < n_slices; ++s) {
+            const int kc = min(M::KC, d.K - s * M::KC);
             mbar_wait(&full_bar[st], ph);
-            t_wait += clock64() - tw0;
-          }
-          if (ct * 8 < kc) {
-            const uint8_t* src = ring + (size_t)st * M::STAGE_BYTES + ct * 16;
-            float xf[BMAX][8];
+            if (ct * 8 < kc) {
+              const uint8_t* src = ring + (size_t)st * M::STAGE_BYTES + ct * 16;
+              float xf[BMAX][8];
 #pragma unroll
-            for (int b = 0; b < BMAX; ++b) {
-              const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * p.Kmax + (size_t)s * M::KC + ct * 8);
-              xf[b][0] = bf16_lo(xv.x); xf[b][1] = bf16_hi(xv.x); xf[b][2] = bf16_lo(xv.y); xf[b][3] = bf16_hi(xv.y);
-              xf[b][4] = bf16_lo(xv.z); xf[b][5] = bf16_hi(xv.z); xf[b][6] = bf16_lo(xv.w); xf[b][7] = bf16_hi(xv.w);
-            }
+              for (int b = 0; b < BMAX; ++b) {
+                const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * p.Kmax + (size_t)s * M::KC + ct * 8);
+                xf[b][0] = bf16_lo(xv.x); xf[b][1] = bf16_hi(xv.x); xf[b][2] = bf16_lo(xv.y); xf[b][3] = bf16_hi(xv.y);
+                xf[b][4] = bf16_lo(xv.z); xf[b][5] = bf16_hi(xv.z); xf[b][6] = bf16_lo(xv.w); xf[b][7] = bf16_hi(xv.w);
+              }
 #pragma unroll
-            for (int r = 0; r < M::ROWS; ++r) {
-              if (r < rows) {
-                const uint4 wv = *reinterpret_cast<const uint4*>(src + r * (M::KC * 2));
-                const float wf[8] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y),
-                                     bf16_lo(wv.z), bf16_hi(wv.z), bf16_lo(wv.w), bf16_hi(wv.w)};
+              for (int r = 0; r < M::ROWS; ++r) {
+                if (r < rows) {
+                  const uint4 wv = *reinterpret_cast<const uint4*>(src + r * (M::KC * 2));
+                  const float wf[8] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y),
+                                       bf16_lo(wv.z), bf16_hi(wv.z), bf16_lo(wv.w), bf16_hi(wv.w)};
 #pragma unroll
-                for (int b = 0; b < BMAX; ++b)
+                  for (int b = 0; b < BMAX; ++b)
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) acc[r * BMAX + b] = fmaf(wf[e], xf[b][e], acc[r * BMAX + b]);
+                    for (int e = 0; e < 8; ++e) acc[r * BMAX + b] = fmaf(wf[e], xf[b][e], acc[r * BMAX + b]);
+                }
               }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+            if (++st == p.n_stages) { st = 0; ph ^= 1; }
+          }
+          warp_reduce_scatter<NV>(acc, lane);
+          const int slot = unit_no & (M::RED_SLOTS - 1);
+          const uint32_t round = (unit_no / M::RED_SLOTS) & 1;
+          mbar_wait(&red_empty[slot], round ^ 1);           // the finalize warp has drained this slot (4 units ago)
+          if ((lane & (32 / NV - 1)) == 0) red[(slot * 16 + cw) * NV + lane / (32 / NV)] = acc[0];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&red_full[slot]);
+        }
+      } else {
+        // ===== finalize warp: sum the 16 partials of each unit, fused epilogue =====
+        constexpr unsigned kMask = (NV == 32) ? 0xffffffffu : ((1u << NV) - 1u);
+        for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
+          const int n0 = g * M::ROWS;
+          const int slot = unit_no & (M::RED_SLOTS - 1);
+          const uint32_t round = (unit_no / M::RED_SLOTS) & 1;
+          const int r = lane / BMAX, b = lane % BMAX, n = n0 + r;
+          const bool ok = lane < NV && b < p.B && n < d.N;
+          // operands of the epilogue are fetched while the compute warps are still busy with this unit
+          float pre0 = 0.f, pre1 = 0.f;
+          if (ok) {
+            if (d.type == PH_OPROJ || d.type == PH_DOWN) pre0 = ldcg_bf16(d.out + (size_t)b * d.N + n);
+            else if (d.type == PH_QKV && n < 2 * p.H) {
+              const float2 cs = __ldg(p.rope + (size_t)pos * 64 + ((n & 127) >> 1));
+              pre0 = cs.x;
+              pre1 = cs.y;
+            }
+          }
+          mbar_wait(&red_full[slot], round);
+          float t = 0.f;
+          if (lane < NV) {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) t += red[(slot * 16 + w) * NV + lane];
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[st]);
-          if (++st == p.n_stages) { st = 0; ph ^= 1; }
-        }
-        warp_reduce_scatter<NV>(acc, lane);
-        float* redp = red + par * (16 * NV);
-        if ((lane & (32 / NV - 1)) == 0) redp[cw * NV + lane / (32 / NV)] = acc[0];
-        asm volatile("bar.sync 2, 512;" ::: "memory");
-        if (ct < NV) {                  // ct == r*BMAX + b, all inside consumer warp 0
-          float t = 0.f;
+          if (lane == 0) mbar_arrive(&red_empty[slot]);
+          if (lane < NV) {
+            if (d.type == PH_OPROJ || d.type == PH_DOWN) {
+              if (ok) d.out[(size_t)b * d.N + n] = __float2bfloat16_rn(t + pre0);
+            } else if (d.type == PH_LOGITS) {
+              const float y = t * rstd_s[b];
+              if (ok && p.logits != nullptr) p.logits[(size_t)b * d.N + n] = y;
+              float bv = ok ? y : -INFINITY;
+              int bi = n;
 #pragma unroll
-          for (int w = 0; w < 16; ++w) t += redp[w * NV + ct];
-          const int r = ct / BMAX, b = ct % BMAX, n = n0 + r;
-          const bool ok = b < p.B && n < d.N;
-          constexpr unsigned kMask = (NV == 32) ? 0xffffffffu : ((1u << NV) - 1u);
-          if (d.type == PH_OPROJ || d.type == PH_DOWN) {
-            if (ok) d.out[(size_t)b * d.N + n] = __float2bfloat16_rn(t + ldcg_bf16(d.out + (size_t)b * d.N + n));
-          } else if (d.type == PH_LOGITS) {
-            const float y = t * rstd_s[b];
-            if (ok && p.logits != nullptr) p.logits[(size_t)b * d.N + n] = y;
-            float bv = ok ? y : -INFINITY;
-            int bi = n;
-#pragma unroll
-            for (int o = BMAX; o < NV; o <<= 1) {
-              const float ov = __shfl_xor_sync(kMask, bv, o);
-              const int oi = __shfl_xor_sync(kMask, bi, o);
-              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (ct < BMAX && ct < p.B && bv > bestv[ct]) {
-              bestv[ct] = bv;
-              besti[ct] = bi;
-            }
-          } else {
-            const float mine = t * rstd_s[b];
-            const float other = __shfl_xor_sync(kMask, mine, BMAX);
-            if ((r & 1) == 0 && ok && n + 1 < d.N) {
-              float x0 = mine, x1 = other;
-              if (d.type == PH_GATEUP) {
-                const float gte = bf16_round(x0), up = bf16_round(x1);      // HF:modeling_llama.py:182-184 rounds both
-                d.out[(size_t)b * (d.N >> 1) + (n >> 1)] = __float2bfloat16_rn(bf16_round(gte / (1.f + __expf(-gte))) * up);
-              } else {
-                const int which = n / p.H, nh = n - which * p.H, head = nh >> 7, cidx = nh & 127;
-                if (which < 2) {
-                  const float2 cs = p.rope[(size_t)pos * 64 + (cidx >> 1)];
-                  const float a = x0 * cs.x - x1 * cs.y, c2 = x1 * cs.x + x0 * cs.y;
-                  x0 = a;
-                  x1 = c2;
+              for (int o = BMAX; o < NV; o <<= 1) {
+                const float ov = __shfl_xor_sync(kMask, bv, o);
+                const int oi = __shfl_xor_sync(kMask, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+              }
+              if (lane < BMAX && lane < p.B && bv > bestv[lane]) {
+                bestv[lane] = bv;
+                besti[lane] = bi;
+              }
+            } else {
+              const float mine = t * rstd_s[b];
+              const float other = __shfl_xor_sync(kMask, mine, BMAX);
+              if ((r & 1) == 0 && ok && n + 1 < d.N) {
+                float x0 = mine, x1 = other;
+                if (d.type == PH_GATEUP) {
+                  const float gte = bf16_round(x0), up = bf16_round(x1);      // HF:modeling_llama.py:182-184 rounds both
+                  d.out[(size_t)b * (d.N >> 1) + (n >> 1)] = __float2bfloat16_rn(bf16_round(gte / (1.f + __expf(-gte))) * up);
+                } else {
+                  const int which = n / p.H, nh = n - which * p.H, head = nh >> 7, cidx = nh & 127;
+                  if (which < 2) {
+                    const float a = x0 * pre0 - x1 * pre1, c2 = x1 * pre0 + x0 * pre1;   // (cos, sin) prefetched
+                    x0 = a;
+                    x1 = c2;
+                  }
+                  __nv_bfloat16* dst;
+                  if (which == 0) dst = d.out + (size_t)b * p.H + nh;
+                  else dst = ((which == 1) ? d.kcache : d.vcache) + (((size_t)b * p.nH + head) * p.Smax + pos) * 128 + cidx;
+                  *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x0, x1);
                 }
-                __nv_bfloat16* dst;
-                if (which == 0) dst = d.out + (size_t)b * p.H + nh;
-                else dst = ((which == 1) ? d.kcache : d.vcache) + (((size_t)b * p.nH + head) * p.Smax + pos) * 128 + cidx;
-                *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x0, x1);
               }
             }
           }
         }
       }
+      t_loop += clock64() - t0;
     }
-    if (d.type == PH_ATTN) t_attn += clock64() - t0; else t_loop += clock64() - t0;
     t0 = clock64();
-    if (pi == p.n_phases - 1) {
-      asm volatile("bar.sync 2, 512;" ::: "memory");
-      if (ct < p.B) {
-        p.part_val[(size_t)ct * gridDim.x + blockIdx.x] = bestv[ct];
-        p.part_idx[(size_t)ct * gridDim.x + blockIdx.x] = besti[ct];
-      }
+    if (pi == p.n_phases - 1 && is_fin && lane < p.B) {
+      p.part_val[(size_t)lane * gridDim.x + blockIdx.x] = bestv[lane];
+      p.part_idx[(size_t)lane * gridDim.x + blockIdx.x] = besti[lane];
     }
     grid_sync_consumers(p.grid_counter, (++sync_no) * gridDim.x, ct);
     t_sync += clock64() - t0;
   }
   if (p.dbg != nullptr && ct == 0) {
     long long* o = p.dbg + (size_t)blockIdx.x * 8;
-    o[0] = t_sync; o[1] = t_stage; o[2] = t_loop; o[3] = t_attn; o[4] = t_wait;
+    o[0] = t_sync; o[1] = t_stage; o[2] = t_loop; o[3] = t_attn; o[4] = 0;
   }
 
   // ---- greedy arg-max over the per-CTA partials (lowest index on ties, like torch.argmax); advance the counters ----
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && !is_fin) {
     if (cw < p.B) {
       const int b = cw;
       float bv = -INFINITY;
@@ -438,7 +473,7 @@ __global__ void __launch_bounds__(544, 1) decode_step_kernel(const StepParams p)
         if (p.out_tokens != nullptr) p.out_tokens[(size_t)b * p.out_stride + *p.step] = bi;
       }
     }
-    asm volatile("bar.sync 2, 512;" ::: "memory");
+    asm volatile("bar.sync 7, 512;" ::: "memory");
     if (ct == 0) {
       *p.step += 1;
       *p.seq_len += 1;
