@@ -164,14 +164,14 @@ static inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); 
 // TMA descriptors
 // ------------------------------------------------------------------------------------------------
 static int make_tmap_2d(vly_ctx* c, CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
-                        uint32_t box_inner, uint32_t box_rows) {
+                        uint32_t box_inner, uint32_t box_rows, bool swizzle128 = true) {
   cuuint64_t dims[2] = {inner, rows};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(VLY_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d (ptr=%p inner=%llu rows=%llu stride=%llu box=%u,%u)", (int)r, ptr,
                 (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_inner, box_rows);
@@ -593,6 +593,11 @@ extern "C" int vly_finalize_weights(vly_ctx* c) {
 // ------------------------------------------------------------------------------------------------
 // ViT encode
 // ------------------------------------------------------------------------------------------------
+static long long* g_attn_dbg = nullptr;
+extern "C" int vly_debug_attn_counters(long long* host_out, int n) {
+  if (!g_attn_dbg) return -1;
+  return cudaMemcpy(host_out, g_attn_dbg, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
 static int launch_vit_attention(vly_ctx* c, const bf16* qkv, int F, bf16* out, cudaStream_t st) {
   const vly_config& g = c->cfg;
   const int D = g.vit_hidden, tokens = (g.vit_image / g.vit_patch) * (g.vit_image / g.vit_patch) + 1;
@@ -612,8 +617,28 @@ static int launch_vit_attention(vly_ctx* c, const bf16* qkv, int F, bf16* out, c
   p.D = D;
   p.ctx = out;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
+  {
+    static long long* dbg = nullptr;
+    if (getenv("VLY_ATTN_DBG") && !dbg) { CK(cudaMalloc((void**)&dbg, 148 * 16 * 8)); CK(cudaMemset(dbg, 0, 148 * 16 * 8)); }
+    p.dbg = dbg;
+    g_attn_dbg = dbg;
+  }
   const int items = F * g.vit_heads;
   const int grid = items < c->num_sms ? items : c->num_sms;
+  static const bool v1 = getenv("VLY_VIT_ATTN_V1") != nullptr;
+  if (!v1) {
+    static bool attr2 = false;
+    if (!attr2) {
+      CK(cudaFuncSetAttribute(vit_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VitAttnPPCfg::SMEM_BYTES));
+      attr2 = true;
+    }
+    CUtensorMap tx;
+    TRY(make_tmap_2d(c, &tx, qkv, 3 * D, (uint64_t)F * tokens, (uint64_t)3 * D * 2, 64, 1, /*swizzle128=*/false));   // single rows, read linearly
+    vit_attention_pp_kernel<<<grid, VitAttnPPCfg::THREADS, VitAttnPPCfg::SMEM_BYTES, st>>>(tq, tx, p);
+    c->launches++;
+    CKL();
+    return VLY_OK;
+  }
   vit_attention_kernel<<<grid, VitAttnCfg::THREADS, VitAttnCfg::SMEM_BYTES, st>>>(tq, tkv, p);
   c->launches++;
   CKL();

@@ -34,6 +34,7 @@ struct VitAttnParams {
   int D;                    // 1024
   __nv_bfloat16* ctx;       // [F*tokens, D]
   float scale_log2e;        // head_dim^-0.5 * log2(e)
+  long long* dbg;           // optional cycle counters (profiling aid)
 };
 
 struct VitAttnCfg {
@@ -391,6 +392,13 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);
+      // descriptors are built once; the issue loop only advances their 16-byte-unit address field
+      const uint64_t desc_q = make_smem_desc_sw128(base_u32 + C::OFF_Q, 16, 1024);
+      const uint64_t desc_p = make_smem_desc_sw128(base_u32 + C::OFF_P, 16, 1024);
+      const uint64_t desc_k[2] = {make_smem_desc_sw128(base_u32 + C::OFF_K, 16, 1024),
+                                  make_smem_desc_sw128(base_u32 + C::OFF_K + 2 * C::TILE_BYTES, 16, 1024)};
+      const uint64_t desc_v[2] = {make_smem_desc_sw128(base_u32 + C::OFF_V, C::TILE_BYTES, 1024),
+                                  make_smem_desc_sw128(base_u32 + C::OFF_V + 2 * C::TILE_BYTES, C::TILE_BYTES, 1024)};
       mbar_wait(q_full, 0);
       int st = 0;
       uint32_t ph = 0, se_ph = 0, pf_ph = 0;
@@ -400,13 +408,13 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
         mbar_wait(s_empty, se_ph ^ 1);   // softmax finished reading the previous S
         se_ph ^= 1;
         tc_fence_after();
-        const uint32_t q_addr = base_u32 + C::OFF_Q;
-        const uint32_t k_addr = base_u32 + C::OFF_K + st * 2 * C::TILE_BYTES;
+        {
+          const uint64_t dk = desc_k[st];
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * C::TILE_BYTES + (kk & 3) * 32;
-          tc_mma_bf16(tmem_base + 0, make_smem_desc_sw128(q_addr + off, 16, 1024),
-                      make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s, kk != 0);
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t off = uint64_t((kk >> 2) * (C::TILE_BYTES / 16) + (kk & 3) * 2);
+            tc_mma_bf16(tmem_base + 0, desc_q + off, dk + off, idesc_s, kk != 0);
+          }
         }
         tc_commit(s_full);
         if (!pass) {
@@ -415,16 +423,13 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
           mbar_wait(p_full, pf_ph);
           pf_ph ^= 1;
           tc_fence_after();
-          const uint32_t p_addr = base_u32 + C::OFF_P;
-          const uint32_t v_addr = base_u32 + C::OFF_V + st * 2 * C::TILE_BYTES;
+          const uint64_t dv = desc_v[st];
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             // A = P[128 rows, keys kk*16..+16): key block (kk>>2), 32 B per k-step inside the atom
             // B = V[keys kk*16..+16, d 0..127] MN-major: 16 keys = 2 atoms of 1024 B; d chunks 16 KB apart (LBO)
-            tc_mma_bf16(tmem_base + 128,
-                        make_smem_desc_sw128(p_addr + (kk >> 2) * C::TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                        make_smem_desc_sw128(v_addr + kk * 16 * 128, C::TILE_BYTES, 1024), idesc_pv,
-                        (j | kk) != 0);
+            tc_mma_bf16(tmem_base + 128, desc_p + uint64_t((kk >> 2) * (C::TILE_BYTES / 16) + (kk & 3) * 2),
+                        dv + uint64_t(kk * (16 * 128 / 16)), idesc_pv, (j | kk) != 0);
           }
           tc_commit(&kv_empty[st]);
           tc_commit(p_empty);
@@ -532,6 +537,343 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+
+// ============================================================================================
+// ViT attention, generation 2: ping-pong pipeline.
+//   warp 0 (one thread)  : TMA loads + every tcgen05.mma
+//   warps 1-8 / 9-16     : softmax + epilogue warpgroups A / B, two threads per query row (each half of the keys)
+//   TMEM region R (256 columns each): S_R = Q K^T over keys 0..255 (UMMA 128x256x16 x4); O_R (64 columns) aliases the
+//   last 64 columns of S_R once P_R is complete.  Tiles alternate between the regions, so the softmax of one tile
+//   (MUFU-bound) overlaps the MMAs, TMEM traffic and epilogue of the other.  The 257th key (the CLS/last token)
+//   is handled on CUDA cores -- one 64-wide dot product and one axpy per row -- which keeps the MMA shapes clean
+//   (N = 256, K = 256) and removes the 272-column padding.  K is reloaded for the next (frame, head) as soon as the
+//   item's last S-MMA retires, V when its last P V retires.
+// ============================================================================================
+struct VitAttnPPCfg {
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int KV_BYTES = 256 * 128;
+  static constexpr int P_BYTES = 4 * 128 * 128;            // 256 key columns = 4 blocks of 64
+  static constexpr int OFF_Q = 0;                          // [2]
+  static constexpr int OFF_K = 2 * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_BYTES;           // [2]
+  static constexpr int OFF_X = OFF_P + 2 * P_BYTES;        // 257th key / value rows per region: kx[128 B], vx[2 tile parities][128 B]
+  static constexpr int OFF_XMAX = OFF_X + 2 * 384;         // row max exchange between the two halves: [2 regions][2 halves][128] bf16
+  static constexpr int OFF_XSUM = OFF_XMAX + 1024;         // partial row sum of half 1: [2 regions][128] fp32
+  static constexpr int OFF_BAR = OFF_XSUM + 1024;
+  // 227 KB is the hard limit: there is no room for an alignment slack, the kernel traps if the dynamic shared memory
+  // window is not 1024-byte aligned (it is when the kernel has no static shared memory)
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int THREADS = 544;                      // warp 0 + two softmax warpgroups of 8 warps
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int O_OFF = 192;
+};
+static_assert(VitAttnPPCfg::SMEM_BYTES <= 232448, "ViT attention exceeds 227 KB of shared memory");
+
+// tma_q: 2D over qkv [F*257, 3D], box {64,128};  tma_x: same tensor, box {64,1}
+__global__ void __launch_bounds__(544, 1)
+vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_x, const VitAttnParams p) {
+  using C = VitAttnPPCfg;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  if (base_u32 & 1023u) __trap();          // SWIZZLE_128B operands need 1024-byte alignment; no slack left to fix it up
+  uint8_t* smem = smem_raw;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* k_full = bars + 0;
+  uint64_t* v_full = bars + 1;
+  uint64_t* k_done = bars + 2;
+  uint64_t* v_done = bars + 3;
+  uint64_t* q_full = bars + 4;    // [2]
+  uint64_t* s_full = bars + 6;    // [2]
+  uint64_t* p_full = bars + 8;    // [2]
+  uint64_t* o_full = bars + 10;   // [2]
+  uint64_t* r_free = bars + 12;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items_total = p.F * p.heads;
+  const int my_items = (n_items_total > (int)blockIdx.x) ? (n_items_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_tiles = my_items * 3;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_x);
+    mbar_init(k_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(k_done, 1);
+    mbar_init(v_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&r_free[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_tiles > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      const uint64_t desc_q[2] = {make_smem_desc_sw128(base_u32 + C::OFF_Q, 16, 1024), make_smem_desc_sw128(base_u32 + C::OFF_Q + C::Q_BYTES, 16, 1024)};
+      const uint64_t desc_p[2] = {make_smem_desc_sw128(base_u32 + C::OFF_P, 16, 1024), make_smem_desc_sw128(base_u32 + C::OFF_P + C::P_BYTES, 16, 1024)};
+      const uint64_t desc_k = make_smem_desc_sw128(base_u32 + C::OFF_K, 16, 1024);
+      const uint64_t desc_v = make_smem_desc_sw128(base_u32 + C::OFF_V, 16, 1024);
+      uint32_t kf_ph = 0, vf_ph = 0, kd_ph = 0, vd_ph = 0, q_ph[2] = {0, 0}, p_ph[2] = {0, 0}, rf_ph[2] = {0, 0};
+      long long w_vf = 0, w_pf = 0, w_vd = 0, w_rf = 0, w_kf = 0, w_qf = 0, w_kd = 0, x_mma = 0, x_tma = 0; const long long t_begin = clock64();
+      auto item_of = [&](int g) { return (int)blockIdx.x + (g / 3) * (int)gridDim.x; };
+      auto load_k = [&](int item, int par) {
+        const int f = item / p.heads, h = item % p.heads, row0 = f * p.tokens;
+        mbar_expect_tx(k_full, C::KV_BYTES);
+        tma_load_2d(smem + C::OFF_K, &tma_q, k_full, p.D + h * 64, row0);
+        tma_load_2d(smem + C::OFF_K + 128 * 128, &tma_q, k_full, p.D + h * 64, row0 + 128);
+      };
+      auto load_v = [&](int item, int par) {
+        const int f = item / p.heads, h = item % p.heads, row0 = f * p.tokens;
+        mbar_expect_tx(v_full, C::KV_BYTES);
+        tma_load_2d(smem + C::OFF_V, &tma_q, v_full, 2 * p.D + h * 64, row0);
+        tma_load_2d(smem + C::OFF_V + 128 * 128, &tma_q, v_full, 2 * p.D + h * 64, row0 + 128);
+      };
+      auto back = [&](int t) {     // O = P V for tile t
+        const int R = t & 1;
+        if (t % 3 == 0) {          // first tile of an item: its V must have landed
+          { const long long tq_ = clock64(); mbar_wait(v_full, vf_ph); w_vf += clock64() - tq_; }
+          vf_ph ^= 1;
+        }
+        { const long long tq_ = clock64(); mbar_wait(&p_full[R], p_ph[R]); w_pf += clock64() - tq_; }
+        p_ph[R] ^= 1;
+        tc_fence_after();
+        // the single issuing thread must sustain one MMA per ~32 cycles here (N = 64): descriptors are precomputed and
+        // only their 16-byte-unit address field is advanced by compile-time constants
+        const uint64_t dp0 = desc_p[R];
+        const uint32_t d_o = tmem_base + R * 256 + C::O_OFF;
+        const long long tm_ = clock64();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          tc_mma_bf16(d_o, dp0 + uint64_t((j >> 2) * (128 * 128 / 16) + (j & 3) * 2), desc_v + uint64_t(j * (16 * 128 / 16)), idesc_pv, j != 0);
+        tc_commit(&o_full[R]);
+        x_mma += clock64() - tm_;
+        if (t % 3 == 2) tc_commit(v_done);      // every P V of the item has been issued
+      };
+      // Q tile + the 257th key / value rows of the (frame, head) travel together on the region's q_full barrier.  They are
+      // issued one tile AHEAD: Q_R / X_R[parity] are free as soon as p_full of the region's previous tile was observed.
+      auto issue_q = [&](int g) {
+        const int R = g & 1, qt = g % 3, item = item_of(g);
+        const int f = item / p.heads, h = item % p.heads, row0 = f * p.tokens;
+        uint8_t* xr = smem + C::OFF_X + R * 384;       // kx: read before p_full; vx: read in the epilogue -> double buffered
+        mbar_expect_tx(&q_full[R], C::Q_BYTES + 256);
+        tma_load_2d(smem + C::OFF_Q + R * C::Q_BYTES, &tma_q, &q_full[R], h * 64, row0 + qt * 128);
+        tma_load_2d(xr, &tma_x, &q_full[R], p.D + h * 64, row0 + 256);
+        tma_load_2d(xr + 128 + ((g >> 1) & 1) * 128, &tma_x, &q_full[R], 2 * p.D + h * 64, row0 + 256);
+      };
+      load_k(item_of(0), 0);
+      load_v(item_of(0), 0);
+      issue_q(0);
+      for (int g = 0; g < n_tiles; ++g) {
+        const int R = g & 1, qt = g % 3, item = item_of(g);
+        if (qt == 0 && g > 0) {
+          // the previous item's last P V is still pending: issue it, then its V buffer can be refilled
+          back(g - 1);
+          { const long long tq_ = clock64(); mbar_wait(v_done, vd_ph); w_vd += clock64() - tq_; }
+          vd_ph ^= 1;
+          load_v(item, (g / 3) & 1);
+        }
+        { const long long tq_ = clock64(); mbar_wait(&r_free[R], rf_ph[R] ^ 1); w_rf += clock64() - tq_; }     // region R (S/O columns, Q_R, P_R) released by the epilogue of tile g-2
+        rf_ph[R] ^= 1;
+        if (qt == 0) {
+          { const long long tq_ = clock64(); mbar_wait(k_full, kf_ph); w_kf += clock64() - tq_; }
+          kf_ph ^= 1;
+        }
+        { const long long tq_ = clock64(); mbar_wait(&q_full[R], q_ph[R]); w_qf += clock64() - tq_; }
+        q_ph[R] ^= 1;
+        tc_fence_after();
+        {
+          const uint64_t dq = desc_q[R];
+          const long long tm_ = clock64();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_base + R * 256, dq + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
+          tc_commit(&s_full[R]);
+          x_mma += clock64() - tm_;
+        }
+        if (qt == 2) {
+          tc_commit(k_done);
+          if (g + 1 < n_tiles) {                 // refill K for the next item while this item's softmax / P V run
+            { const long long tq_ = clock64(); mbar_wait(k_done, kd_ph); w_kd += clock64() - tq_; }
+            kd_ph ^= 1;
+            load_k(item_of(g + 1), ((g + 1) / 3) & 1);
+          }
+        }
+        if (qt != 0 && g > 0) back(g - 1);       // (for qt == 0 it was issued above)
+        if (g + 1 < n_tiles) { const long long tt_ = clock64(); issue_q(g + 1); x_tma += clock64() - tt_; }   // p_full(g-1) observed -> the other region's Q buffer is free
+      }
+      back(n_tiles - 1);
+      // all MMAs must retire before the CTA exits / TMEM is released
+      mbar_wait(v_done, vd_ph);
+      if (p.dbg) { long long* o = p.dbg + (size_t)blockIdx.x * 16; o[0] = clock64() - t_begin; o[1] = w_rf; o[2] = w_qf; o[3] = w_kf; o[4] = w_kd; o[5] = w_pf; o[6] = x_mma; o[7] = x_tma; }
+    }
+  } else {
+    // ================= softmax + epilogue warpgroups: 8 warps each, TWO threads per query row =================
+    // thread (row r, half hf) owns key columns [128*hf, 128*hf+128) of S; half 0 also owns the 257th key and the epilogue.
+    const int R = (warp - 1) >> 3;           // 0: warps 1-8, 1: warps 9-16
+    const int hf = ((warp - 1) >> 2) & 1;
+    const int quad = warp & 3;               // TMEM lane quadrant is fixed by the hardware warp id
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const uint32_t treg = tmem_base + R * 256 + lane_addr;
+    uint32_t s_ph = 0, o_ph = 0, q_ph = 0;
+    long long g_sf = 0, g_of = 0, g_bar = 0; const long long g_begin = clock64();
+    uint8_t* sP = smem + C::OFF_P + R * C::P_BYTES;
+    const uint8_t* sQ = smem + C::OFF_Q + R * C::Q_BYTES;
+    __nv_bfloat16* xmax = reinterpret_cast<__nv_bfloat16*>(smem + C::OFF_XMAX) + R * 256;   // [2 halves][128]
+    float* xsum = reinterpret_cast<float*>(smem + C::OFF_XSUM) + R * 128;                    // [128] (written by half 1)
+    for (int g = R; g < n_tiles; g += 2) {
+      const int qt = g % 3, it = g / 3, item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int f = item / p.heads, h = item % p.heads;
+      const int qrow = qt * 128 + r;
+      const bool warp_active = (qt * 128 + quad * 32) < p.tokens;
+      const __nv_bfloat16* kx = reinterpret_cast<const __nv_bfloat16*>(smem + C::OFF_X + R * 384);
+      const __nv_bfloat16* vx = kx + 64 + ((g >> 1) & 1) * 64;
+      __syncwarp();
+      const long long ts_ = clock64();
+      mbar_wait(&q_full[R], q_ph);           // Q tile and the extra key/value row of this tile are in shared memory
+      q_ph ^= 1;
+      mbar_wait(&s_full[R], s_ph);
+      g_sf += clock64() - ts_;
+      s_ph ^= 1;
+      tc_fence_after();
+      float mx = -INFINITY, s_x = 0.f;
+      if (warp_active) {
+        if (hf == 0) {
+          // score against the 257th key on CUDA cores: q row from the swizzled Q tile
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 qv = *reinterpret_cast<const uint4*>(sQ + r * 128 + ((j ^ (r & 7)) << 4));
+            const uint4 kv = *reinterpret_cast<const uint4*>(kx + j * 8);
+            s_x += bf16_lo(qv.x) * bf16_lo(kv.x) + bf16_hi(qv.x) * bf16_hi(kv.x) + bf16_lo(qv.y) * bf16_lo(kv.y) + bf16_hi(qv.y) * bf16_hi(kv.y) +
+                   bf16_lo(qv.z) * bf16_lo(kv.z) + bf16_hi(qv.z) * bf16_hi(kv.z) + bf16_lo(qv.w) * bf16_lo(kv.w) + bf16_hi(qv.w) * bf16_hi(kv.w);
+          }
+          mx = s_x;
+        }
+        // TMEM loads are asynchronous until tcgen05.wait::ld: keep the NEXT 32-column chunk in flight while the
+        // current one is processed (two register buffers), instead of paying the TMEM round trip per chunk
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(treg + hf * 128, va);
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32(treg + hf * 128 + (c + 1) * 32, vb);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
+          tmem_ld_wait();
+          if (c + 2 < 4) tmem_ld_32x32(treg + hf * 128 + (c + 2) * 32, va);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
+        }
+      }
+      // both halves must subtract the SAME offset: each rounds its own max to bf16 and takes the max of the two rounded
+      // values (any common offset within a few % of the true max is numerically fine; the sums use it consistently)
+      const __nv_bfloat16 mxb = __float2bfloat16_rn(mx);
+      xmax[hf * 128 + r] = mxb;
+      { const long long tb_ = clock64(); asm volatile("bar.sync %0, 256;" ::"r"(1 + R) : "memory"); g_bar += clock64() - tb_; }
+      float part = 0.f, p_x = 0.f;
+      if (warp_active) {
+        mx = fmaxf(__bfloat162float(mxb), __bfloat162float(xmax[(hf ^ 1) * 128 + r]));
+        const float mb = mx * p.scale_log2e;
+        auto exp_store = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              e[i] = fast_exp2(fmaf(__uint_as_float(v[8 * j + i]), p.scale_log2e, -mb));
+              part += e[i];
+            }
+            st_sw128_row16(sP, 128, r, hf * 128 + c * 32 + j * 8,
+                           make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7])));
+          }
+        };
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(treg + hf * 128, va);
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32(treg + hf * 128 + (c + 1) * 32, vb);
+          exp_store(va, c);
+          tmem_ld_wait();
+          if (c + 2 < 4) tmem_ld_32x32(treg + hf * 128 + (c + 2) * 32, va);
+          exp_store(vb, c + 1);
+        }
+        if (hf == 0) {
+          p_x = fast_exp2(fmaf(s_x, p.scale_log2e, -mb));
+          part += p_x;
+        } else {
+          xsum[r] = part;
+        }
+      } else {
+        for (int col = 0; col < 128; col += 8) st_sw128_row16(sP, 128, r, hf * 128 + col, make_uint4(0, 0, 0, 0));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[R]);               // (release) also publishes xsum to half 0: p_full -> T0 -> o_full -> half 0
+
+      if (hf == 0) {
+        __syncwarp();
+        { const long long to_ = clock64(); mbar_wait(&o_full[R], o_ph); g_of += clock64() - to_; }
+        o_ph ^= 1;
+        tc_fence_after();
+        if (warp_active) {
+          const float inv = __frcp_rn(part + xsum[r]);
+          __nv_bfloat16* dst = p.ctx + ((size_t)f * p.tokens + qrow) * p.D + h * 64;
+          uint32_t vo[2][32];
+          tmem_ld_32x32(treg + C::O_OFF, vo[0]);
+          tmem_ld_32x32(treg + C::O_OFF + 32, vo[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t (&v)[32] = vo[c];
+            if (qrow < p.tokens) {
+              float o[32];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 vv = *reinterpret_cast<const uint4*>(vx + c * 32 + j * 8);
+                const float xv[8] = {bf16_lo(vv.x), bf16_hi(vv.x), bf16_lo(vv.y), bf16_hi(vv.y), bf16_lo(vv.z), bf16_hi(vv.z), bf16_lo(vv.w), bf16_hi(vv.w)};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[j * 8 + e] = fmaf(p_x, xv[e], __uint_as_float(v[j * 8 + e])) * inv;
+              }
+              uint4* op = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                op[j] = make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
+                                   pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+            }
+          }
+        }
+        __syncwarp();
+        tc_fence_before();
+        mbar_arrive(&r_free[R]);
+      }
+    }
+    if (p.dbg && hf == 0 && r == 0) { long long* o = p.dbg + (size_t)blockIdx.x * 16 + 8 + R * 4; o[0] = clock64() - g_begin; o[1] = g_sf; o[2] = g_bar; o[3] = g_of; }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
