@@ -80,6 +80,21 @@ int vly_finalize_weights(vly_ctx* ctx);
 int vly_vit_encode(vly_ctx* ctx, const void* pixels_dev, int pixel_dtype, int n_frames, int select_layer, void* out_dev,
                    void* stream);
 
+/* ---- fused ViT encode + all-gather of frame features (multi-GPU; BASELINE north_star "all-gather of frame embeddings before
+ * projection").  The reference has no inference collective; torch.distributed/NCCL is the plain path
+ * (valley_b200/dist.py); this is the fused one: the LAST ViT layer's fc2+residual epilogue stores every finished tile
+ * into the gather buffer of every rank over NVLink (peer-mapped pointers), followed by a flag exchange.
+ *   vly_gather_create     : allocate this rank's gather buffer [rows_total, 1024] bf16 (+flags) and export its 64-byte CUDA IPC handle
+ *   vly_gather_open_peers : map all ranks' buffers (handles gathered by the caller, e.g. torch.distributed.all_gather_object)
+ *   vly_vit_encode_gather : encode n_frames local frames that start at global frame index frame_offset; on return (stream
+ *                           order) the local gather buffer holds the features of ALL ranks' frames */
+int vly_gather_create(vly_ctx* ctx, int64_t rows_total, void** local_buf_dev, void* ipc_handle_out_64B);
+int vly_gather_open_peers(vly_ctx* ctx, const void* handles_64B_each, int world, int rank);
+int vly_vit_encode_gather(vly_ctx* ctx, const void* pixels_dev, int pixel_dtype, int n_frames, int frame_offset, int select_layer,
+                          void* stream);
+/* enqueue after the kernels that read the gather buffer: lets the peers overwrite it in their next vly_vit_encode_gather */
+int vly_gather_release(vly_ctx* ctx, void* stream);
+
 /* ---- mm_projector over every token, == encode_images' projection (valley_model.py:187-190):
  * feats [rows,1024] bf16 -> out [rows,hidden] bf16 */
 int vly_project(vly_ctx* ctx, const void* feats_dev, int64_t rows, void* out_dev, void* stream);

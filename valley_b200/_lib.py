@@ -45,6 +45,10 @@ SIGNATURES = {
     "vly_load_weight": (_i, [_vp, C.c_char_p, _vp, _i, _p(_i64), _i]),
     "vly_finalize_weights": (_i, [_vp]),
     "vly_vit_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "vly_gather_create": (_i, [_vp, _i64, _p(_vp), _vp]),
+    "vly_gather_open_peers": (_i, [_vp, _vp, _i, _i]),
+    "vly_vit_encode_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "vly_gather_release": (_i, [_vp, _vp]),
     "vly_project": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "vly_pool_project": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "vly_build_splice_map": (_i, [_p(_i64), _i, _i, _i, _p(VlyTokens), _p(C.c_int32), _p(C.c_int32)]),

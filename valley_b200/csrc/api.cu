@@ -112,6 +112,14 @@ struct vly_ctx {
   Buf w_col, w_patch, w_qkv, w_ctx, w_h, w_stats, w_pool, w_x, w_q, w_attn, w_hb, w_pstats;
   cudaStream_t cap_stream = nullptr;
   int64_t launches = 0;
+  // fused all-gather state
+  bf16* g_buf = nullptr;          // [g_rows, vit_hidden] + flags
+  int64_t g_rows = 0;
+  int* g_flags = nullptr;
+  bf16* g_peer_buf[8] = {};
+  int* g_peer_flags[8] = {};
+  int g_world = 0, g_rank = 0, g_epoch = 0;
+  Buf w_xlocal;
 };
 
 struct vly_kv {
@@ -652,9 +660,17 @@ static int vit_layers_needed(const vly_config& g, int select_layer, int* out) {
   return VLY_OK;
 }
 
+static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int select_layer, void* out_dev, void* stream,
+                           bool gather, long long gather_row_off);
+
 extern "C" int vly_vit_encode(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int select_layer, void* out_dev, void* stream) {
   if (!c || !pixels || !out_dev || F <= 0) return fail(VLY_ERR_INVALID, "vly_vit_encode: bad argument");
   std::lock_guard<std::mutex> lk(c->mu);
+  return vit_encode_impl(c, pixels, pixel_dtype, F, select_layer, out_dev, stream, false, 0);
+}
+
+static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int select_layer, void* out_dev, void* stream,
+                           bool gather, long long gather_row_off) {
   if (!c->finalized || !c->has_vit) return fail(VLY_ERR_STATE, "vly_vit_encode: vision weights not loaded/finalised");
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -721,14 +737,125 @@ extern "C" int vly_vit_encode(vly_ctx* c, const void* pixels, int pixel_dtype, i
         p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / D; p.eps = g.vit_eps;
         TRY(launch_gemm<EPI_LN_BIAS_GELU>(c, pick_bn(MLP), x, D, w.w1, D, p, st));
       }
-      {  // fc2 + residual
+      {  // fc2 + residual (+ on the last layer of a sharded encode: push every tile to all ranks' gather buffers)
         GemmParams p = {};
         p.M = M; p.N = D; p.K = MLP;
         p.out = x; p.ldo = D; p.bias = w.b2; p.residual = x; p.ldr = D; p.stats_out = stats;
+        if (gather && l == n_layers - 1) {
+          p.n_peers = c->g_world;
+          for (int q = 0; q < c->g_world; ++q) p.peer_out[q] = c->g_peer_buf[q];
+          p.peer_row_off = gather_row_off + (long long)f0 * tokens;
+        }
         TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, pick_bn(D), (bf16*)c->w_h.p, MLP, w.w2, MLP, p, st));
       }
     }
+    if (gather && n_layers == 0) return fail(VLY_ERR_INVALID, "vly_vit_encode_gather needs at least one encoder layer (select_layer != 0)");
   }
+  return VLY_OK;
+}
+
+// ---- fused all-gather plumbing ----
+struct PeerFlags { int* p[8]; };
+__global__ void gather_signal_kernel(PeerFlags pf, int world, int rank, int epoch) {
+  if ((int)threadIdx.x < world) {
+    __threadfence_system();                                   // this GPU's peer stores (previous kernels) are performed
+    *reinterpret_cast<volatile int*>(pf.p[threadIdx.x] + rank) = epoch;
+  }
+}
+__global__ void gather_wait_kernel(volatile int* flags, int world, int epoch, int* timeout_flag) {
+  if ((int)threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (flags[threadIdx.x] < epoch) {
+      if (clock64() - t0 > 20000000000LL) { *timeout_flag = 1; break; }   // ~10 s: a peer died
+    }
+    __threadfence_system();
+  }
+}
+
+extern "C" int vly_gather_create(vly_ctx* c, int64_t rows_total, void** local_buf, void* handle_out) {
+  if (!c || rows_total <= 0 || !local_buf || !handle_out) return fail(VLY_ERR_INVALID, "vly_gather_create: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CK(cudaSetDevice(c->cfg.device));
+  if (c->g_buf) return fail(VLY_ERR_STATE, "vly_gather_create: a gather buffer already exists for this context");
+  const size_t data = (((size_t)rows_total * c->cfg.vit_hidden * 2) + 255) & ~size_t(255);
+  void* base;
+  CK(cudaMalloc(&base, data + 256));
+  CK(cudaMemset(base, 0, data + 256));
+  c->g_buf = (bf16*)base;
+  c->g_rows = rows_total;
+  c->g_flags = (int*)((char*)base + data);
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, base));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  memcpy(handle_out, &h, 64);
+  *local_buf = base;
+  return VLY_OK;
+}
+
+extern "C" int vly_gather_open_peers(vly_ctx* c, const void* handles, int world, int rank) {
+  if (!c || !handles || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(VLY_ERR_INVALID, "vly_gather_open_peers: bad argument (world <= 8)");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->g_buf) return fail(VLY_ERR_STATE, "vly_gather_open_peers: call vly_gather_create first");
+  CK(cudaSetDevice(c->cfg.device));
+  const size_t data = (((size_t)c->g_rows * c->cfg.vit_hidden * 2) + 255) & ~size_t(255);
+  for (int q = 0; q < world; ++q) {
+    void* base = nullptr;
+    if (q == rank) base = c->g_buf;
+    else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)handles + (size_t)q * 64, 64);
+      CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->g_peer_buf[q] = (bf16*)base;
+    c->g_peer_flags[q] = (int*)((char*)base + data);
+  }
+  c->g_world = world;
+  c->g_rank = rank;
+  return VLY_OK;
+}
+
+// Tell every rank that this rank has finished reading the current epoch's gather buffer (enqueue after the consumer kernels).
+extern "C" int vly_gather_release(vly_ctx* c, void* stream) {
+  if (!c) return fail(VLY_ERR_INVALID, "null");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->g_world == 0) return fail(VLY_ERR_STATE, "vly_gather_release: no gather group");
+  CK(cudaSetDevice(c->cfg.device));
+  PeerFlags pf;
+  for (int q = 0; q < 8; ++q) pf.p[q] = c->g_peer_flags[q] ? c->g_peer_flags[q] + 8 : nullptr;
+  gather_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, c->g_world, c->g_rank, c->g_epoch);
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+
+extern "C" int vly_vit_encode_gather(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int frame_offset, int select_layer, void* stream) {
+  if (!c || F < 0 || frame_offset < 0 || (F > 0 && !pixels)) return fail(VLY_ERR_INVALID, "vly_vit_encode_gather: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->finalized || !c->has_vit) return fail(VLY_ERR_STATE, "vly_vit_encode_gather: vision weights not loaded/finalised");
+  if (c->g_world == 0) return fail(VLY_ERR_STATE, "vly_vit_encode_gather: call vly_gather_create / vly_gather_open_peers first");
+  const int tokens = (c->cfg.vit_image / c->cfg.vit_patch) * (c->cfg.vit_image / c->cfg.vit_patch) + 1;
+  if (((long long)frame_offset + F) * tokens > c->g_rows) return fail(VLY_ERR_INVALID, "vly_vit_encode_gather: frames [%d,%d) exceed the gather buffer", frame_offset, frame_offset + F);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  static int* timeout_flag = nullptr;
+  if (!timeout_flag) { CK(cudaMalloc((void**)&timeout_flag, 4)); CK(cudaMemset(timeout_flag, 0, 4)); }
+  if (c->g_epoch > 0) {   // every rank must have finished READING the previous epoch before anyone overwrites its buffer
+    gather_wait_kernel<<<1, 32, 0, st>>>(c->g_flags + 8, c->g_world, c->g_epoch, timeout_flag);
+    c->launches++;
+    CKL();
+  }
+  if (F > 0) {
+    TRY(ensure(c->w_xlocal, (size_t)F * tokens * c->cfg.vit_hidden * 2));       // local residual stream (scratch)
+    TRY(vit_encode_impl(c, pixels, pixel_dtype, F, select_layer, c->w_xlocal.p, stream, true, (long long)frame_offset * tokens));
+  }
+  // flag exchange: every rank tells every rank "my rows are in your buffer", then waits for all of them
+  const int epoch = ++c->g_epoch;
+  PeerFlags pf;
+  for (int q = 0; q < 8; ++q) pf.p[q] = c->g_peer_flags[q];
+  gather_signal_kernel<<<1, 32, 0, st>>>(pf, c->g_world, c->g_rank, epoch);
+  gather_wait_kernel<<<1, 32, 0, st>>>(c->g_flags, c->g_world, epoch, timeout_flag);
+  c->launches += 2;
+  CKL();
   return VLY_OK;
 }
 

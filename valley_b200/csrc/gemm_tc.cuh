@@ -49,6 +49,11 @@ struct GemmParams {
   int S, past, H, nH, Smax;       // row m -> (b = m / S, s = m % S), position = past + s
   __nv_bfloat16* kcache;          // [B, nH, Smax, 128] for this layer
   __nv_bfloat16* vcache;
+  // EPI_BIAS_RES_STATS, fused all-gather: besides `out`, every finished row is stored into the gather buffer of every
+  // rank (peer-mapped device pointers, NVLink P2P stores) at row (row + peer_row_off)
+  __nv_bfloat16* peer_out[8];
+  int n_peers;
+  long long peer_row_off;
 };
 
 template <int BN>
@@ -284,6 +289,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) op[j] = o[j];
+          if (p.n_peers > 0) {          // compute + collective in one kernel: the tile is pushed to every rank as it retires
+            for (int q = 0; q < p.n_peers; ++q) {
+              uint4* pp = reinterpret_cast<uint4*>(p.peer_out[q] + (size_t)(row + p.peer_row_off) * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pp[j] = o[j];
+            }
+          }
         } else if constexpr (EPI == EPI_RMS_SWIGLU) {
           uint32_t ow[8];
 #pragma unroll

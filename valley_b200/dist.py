@@ -55,22 +55,70 @@ def encode_frames_sharded(encode_fn: Callable[[torch.Tensor], torch.Tensor], loc
     return gather_frame_features(local, n_frames_total, group)
 
 
+class FusedFrameGather:
+    """Fused ViT-encode + all-gather (include/valley_b200.h: vly_gather_* / vly_vit_encode_gather).
+
+    Each rank owns a gather buffer [n_frames_total*257, 1024] bf16 allocated by the library; CUDA IPC handles are
+    exchanged once through torch.distributed and mapped by every rank.  ``encode`` then runs the local ViT shard whose
+    LAST GEMM epilogue stores each finished tile into every rank's buffer over NVLink (no separate collective kernel),
+    followed by a device-side flag exchange.  ``release`` must be enqueued after the consumers of the buffer."""
+
+    def __init__(self, model, n_frames_total: int, group=None):
+        import ctypes as C
+        from ._lib import check
+        self.model, self.group, self.n_frames_total = model, group, n_frames_total
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.tokens = (model.config.vit_image // model.config.vit_patch) ** 2 + 1
+        rows = n_frames_total * self.tokens
+        buf, handle = C.c_void_p(), C.create_string_buffer(64)
+        check(model._lib.vly_gather_create(model._ctx, rows, C.byref(buf), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        blob = C.create_string_buffer(b"".join(handles), 64 * self.world)
+        check(model._lib.vly_gather_open_peers(model._ctx, blob, self.world, self.rank))
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (rows, model.config.mm_hidden_size), "typestr": "<u2", "data": (buf.value, False), "version": 2}
+        self.features = torch.as_tensor(_Raw(), device=model.device).view(torch.bfloat16).view(n_frames_total, self.tokens, model.config.mm_hidden_size)
+
+    def encode(self, local_pixels: torch.Tensor) -> torch.Tensor:
+        """local_pixels: frames shard_bounds(n_frames_total, world, rank) -> the [n_frames_total,257,1024] buffer (all ranks' features)."""
+        from ._lib import check
+        from .model import _DT
+        lo, hi = shard_bounds(self.n_frames_total, self.world, self.rank)
+        assert local_pixels.shape[0] == hi - lo
+        px = local_pixels if local_pixels.dtype in _DT else local_pixels.float()
+        px = px.to(self.model.device).contiguous()
+        check(self.model._lib.vly_vit_encode_gather(self.model._ctx, px.data_ptr() if hi > lo else None, _DT[px.dtype], hi - lo, lo,
+                                                    getattr(self.model.config, "mm_vision_select_layer", -1), torch.cuda.current_stream().cuda_stream))
+        return self.features
+
+    def release(self):
+        from ._lib import check
+        check(self.model._lib.vly_gather_release(self.model._ctx, torch.cuda.current_stream().cuda_stream))
+
+
 def my_videos(n_videos: int, group=None) -> Tuple[int, int]:
     """Videos whose sequences this rank decodes (LLM replicated per GPU, batch sharded; no further collective)."""
     return shard_bounds(n_videos, dist.get_world_size(group), dist.get_rank(group))
 
 
 def generate_sharded(model, input_ids: torch.Tensor, local_pixels: torch.Tensor, n_videos: int, n_frames: int,
-                     max_new_tokens: int, group=None) -> torch.Tensor:
+                     max_new_tokens: int, group=None, fused: "FusedFrameGather | None" = None) -> torch.Tensor:
     """Config-4 style request: ``n_videos`` videos x ``n_frames`` frames, frames sharded over ranks for the ViT,
     one all-gather, then every rank pools/projects/splices and greedy-decodes its own videos.
     ``input_ids`` [n_videos_local, S] are this rank's prompts; returns this rank's generated ids."""
-    feats = encode_frames_sharded(model.encode_frames, local_pixels, n_videos * n_frames, group)
+    if fused is not None:
+        feats = fused.encode(local_pixels)                    # ViT + gather in one pass over NVLink
+    else:
+        feats = encode_frames_sharded(model.encode_frames, local_pixels, n_videos * n_frames, group)   # plain NCCL all-gather
     lo, hi = my_videos(n_videos, group)
     mine = feats.view(n_videos, n_frames, *feats.shape[1:])[lo:hi].reshape((hi - lo) * n_frames, *feats.shape[1:]).contiguous()
     B = hi - lo
     _, _, _, embeds, _ = model.prepare_inputs_labels_for_multimodal(input_ids, None, None, None, None,
                                                                     frame_features=mine, n_frames=n_frames)
+    if fused is not None:
+        fused.release()                                       # the gather buffer has been consumed (stream order)
     cache = model._borrow_cache(B)
     try:
         S = input_ids.shape[1]
