@@ -215,6 +215,38 @@ static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W
   p.num_m_tiles = cdiv(p.M, 128);
   p.num_n_tiles = cdiv(p.N, BN);
   const int tiles = p.num_m_tiles * p.num_n_tiles;
+  // CTA-pair mode (cta_group::2, 256 x 256 tile per pair): halves the B traffic per SM (64 instead of 96 B/cycle/SM of
+  // L2->SM operand traffic).  Used when there is enough work to fill the pairs; VLY_GEMM_CG2=0/1 overrides.
+  if constexpr (BN == 256) {
+    static const int cg2_env = getenv("VLY_GEMM_CG2") ? atoi(getenv("VLY_GEMM_CG2")) : -1;
+    const int pairs = c->num_sms / 2;
+    const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
+    const bool use_cg2 = cg2_env >= 0 ? (cg2_env == 1) : (pair_tiles >= 2 * pairs);
+    if (use_cg2) {
+      static bool attr2 = false;
+      if (!attr2) {
+        CK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr2 = true;
+      }
+      CUtensorMap tb2;
+      TRY(make_tmap_2d(c, &tb2, W, p.K, p.N, ldw * 2, 64, BN / 2));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (pair_tiles < pairs ? pair_tiles : pairs));
+      cfg.blockDim = dim3(Cfg::THREADS);
+      cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true>, ta, tb2, p));
+      c->launches++;
+      return VLY_OK;
+    }
+  }
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
   gemm_tc_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
   c->launches++;

@@ -73,28 +73,40 @@ struct GemmCfg {
 VLY_DEVINL float quick_gelu_f(float v) { return __fdividef(v, 1.0f + fast_exp2(-2.4554669595930156f * v)); }
 VLY_DEVINL float silu_f(float v) { return __fdividef(v, 1.0f + fast_exp2(-1.4426950408889634f * v)); }
 
-template <int BN, int EPI>
+// CG2 = true: launched as clusters of 2 CTAs; the pair computes a 256 x BN tile with cta_group::2 MMAs (each CTA holds
+// 128 rows of A and BN/2 rows of B per stage and ends up with its own 128 output rows in its own TMEM).
+template <int BN, int EPI, bool CG2 = false>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
-  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK;
+  constexpr int B_ROWS = CG2 ? BN / 2 : BN;                      // rows of B this CTA stages
+  constexpr int B_BYTES = B_ROWS * BK * 2;
+  constexpr int STAGE_BYTES = Cfg::A_BYTES + B_BYTES;
+  constexpr int STAGES = CG2 ? 6 : Cfg::STAGES;                  // 32 KB stages in pair mode
+  static_assert(STAGES * STAGE_BYTES <= Cfg::STAGES * Cfg::STAGE_BYTES, "pair-mode ring must fit the single-CTA budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* svec = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);   // [2][2][BN]
+  float* svec = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // [2][2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + BK - 1) / BK;
+  // work distribution: single CTA -> one 128-row tile per step; pair -> one 256-row tile per step, this CTA owns half
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0;
+  const int num_workers = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int worker = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_m_steps = CG2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+  const int num_tiles = num_m_steps * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -105,11 +117,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], CG2 ? 256 : 128);               // pair mode: both CTAs' epilogues release the leader's accumulator
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if constexpr (CG2) cluster_sync_all();                         // peer barriers are initialised before anyone signals them
+  if (warp == 1) {
+    if constexpr (CG2) tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -120,26 +136,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int m_step = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+        const int m_blk = CG2 ? 2 * m_step + (int)cta_rank : m_step;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if constexpr (CG2) {
+            // both CTAs' bytes are credited to the LEADER's full barrier; only the leader arms it
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            tma_load_2d_cg2(sA + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d_cg2(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN + (int)cta_rank * B_ROWS);
+          } else {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    if (lane == 0 && cta_rank == 0) {                       // pair mode: only the leader CTA issues MMAs
+      constexpr uint32_t idesc = make_idesc_bf16(CG2 ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -147,14 +171,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t da = make_smem_desc_sw128(base_u32 + stage * Cfg::A_BYTES, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(base_u32 + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(base_u32 + STAGES * Cfg::A_BYTES + stage * B_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 K-elements = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CG2) tc_mma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[stage]);                    // frees this smem stage when the MMAs retire
-          if (kb == num_kb - 1) tc_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+          if constexpr (CG2) {
+            tc_commit_cg2(&empty_bar[stage]);                     // frees the stage in BOTH CTAs
+            if (kb == num_kb - 1) tc_commit_cg2(&tmem_full[as]);   // both CTAs' epilogues may read their half
+          } else {
+            tc_commit(&empty_bar[stage]);                    // frees this smem stage when the MMAs retire
+            if (kb == num_kb - 1) tc_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -166,8 +196,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int r_in_tile = quad * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const int m_step = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      const int m_blk = CG2 ? 2 * m_step + (int)cta_rank : m_step;
       const int row = m_blk * BM + r_in_tile;
       const bool row_ok = row < p.M;
 
@@ -225,13 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       float st_sum = 0.f, st_sq = 0.f;
-      constexpr int kChunkUnroll = (EPI == EPI_BIAS_RES_STATS) ? BN / 32 : 1;   // keeps resv[] in registers
-#pragma unroll kChunkUnroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * BN + c * 32, r);
-        tmem_ld_wait();
+      // one 32-column chunk: epilogue math + store
+      auto process_chunk = [&](const uint32_t (&r)[32], const int c) {
         const int n0 = n_blk * BN + c * 32;
         if (row_ok && n0 < p.N) {
         float v[32];
@@ -361,11 +387,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
         }  // row_ok && n0 < N
+      };
+      // TMEM loads are asynchronous until tcgen05.wait::ld: keep the next chunk in flight while this one is processed
+      // (two register buffers) -- with K = 1024 the 8 serialised TMEM round trips of a tile were longer than its main loop
+      const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + as * BN;
+      uint32_t ra[32], rb[32];
+      __syncwarp();
+      tmem_ld_32x32(t_acc, ra);
+      constexpr int kChunkUnroll = (EPI == EPI_BIAS_RES_STATS) ? BN / 64 : 1;   // full unroll keeps resv[] in registers
+#pragma unroll kChunkUnroll
+      for (int c = 0; c < BN / 32; c += 2) {
+        tmem_ld_wait();
+        __syncwarp();
+        tmem_ld_32x32(t_acc + (c + 1) * 32, rb);
+        process_chunk(ra, c);
+        tmem_ld_wait();
+        __syncwarp();
+        if (c + 2 < BN / 32) tmem_ld_32x32(t_acc + (c + 2) * 32, ra);
+        process_chunk(rb, c + 1);
       }
       __syncwarp();
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
+      if constexpr (CG2) {
+        if (cta_rank == 0) mbar_arrive(&tmem_empty[as]);
+        else mbar_arrive_remote(&tmem_empty[as], 0);          // the leader's MMA thread waits for both halves
+      } else {
+        mbar_arrive(&tmem_empty[as]);
+      }
       if constexpr (EPI == EPI_BIAS_RES_STATS) {
         if (row_ok && p.stats_out != nullptr)
           p.stats_out[(size_t)row * p.num_n_tiles + n_blk] = make_float2(st_sum, st_sq);
@@ -376,9 +425,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();     // neither CTA may exit (or free TMEM) while the peer can still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CG2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
