@@ -1344,9 +1344,13 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
     p.dbg = want ? kv->dbg : nullptr;
     g_mega_dbg = kv->dbg;
   }
-  const size_t x_bytes = (((size_t)bmax * p.Kmax * 2) + 127) & ~size_t(127);
-  const size_t misc = MegaCfg::ATTN_SCRATCH + (2 * MegaCfg::MAX_STAGES + 2 * MegaCfg::RED_SLOTS) * 8 + MegaCfg::RED_SLOTS * 16 * 4 * bmax * 4 + 128 * bmax + 512;
-  int n_stages = (int)((226 * 1024 - (long long)x_bytes - (long long)misc) / MegaCfg::STAGE_BYTES);
+  const bool tc = bmax > 1;                                    // tensor-core consumers use padded strides (decode_mega.cuh)
+  const size_t xs_stride_b = tc ? (size_t)(((p.Kmax * 2 + 127) & ~127) + 64) : (size_t)p.Kmax * 2;
+  size_t x_bytes = ((size_t)bmax * xs_stride_b + 127) & ~size_t(127);
+  if (x_bytes < (size_t)MegaCfg::ATTN_SCRATCH) x_bytes = MegaCfg::ATTN_SCRATCH;      // the attention scratch aliases the x block
+  const size_t stage_b = tc ? MegaCfg::STAGE_BYTES_TC : MegaCfg::STAGE_BYTES;
+  const size_t misc = (2 * MegaCfg::MAX_STAGES + 2 * MegaCfg::RED_SLOTS) * 8 + MegaCfg::RED_SLOTS * 16 * 8 * bmax * 4 + 128 * bmax + 512;
+  int n_stages = (int)((226 * 1024 - (long long)x_bytes - (long long)misc) / (long long)stage_b);
   if (n_stages > MegaCfg::MAX_STAGES) n_stages = MegaCfg::MAX_STAGES;
   {
     // measured on B200 (tools/membw.cu): ~96 KB of bulk copies in flight per SM streams at 7.2-7.5 TB/s, 192 KB at 5.2-6 TB/s
@@ -1355,7 +1359,7 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   }
   if (n_stages < 2) return fail(VLY_ERR_INVALID, "decode: activations (B=%d, K=%d) leave no room for the weight ring", B, p.Kmax);
   p.n_stages = n_stages;
-  const size_t smem = (size_t)n_stages * MegaCfg::STAGE_BYTES + x_bytes + misc;
+  const size_t smem = (size_t)n_stages * stage_b + x_bytes + misc;
   CK(cudaMemsetAsync(kv->grid_counter, 0, 4, st));
   void* args[] = {&p};
   cudaError_t e;

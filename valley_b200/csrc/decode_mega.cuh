@@ -65,6 +65,11 @@ struct StepParams {
 struct MegaCfg {
   static constexpr int ROWS = 4, KC = 4096;
   static constexpr int STAGE_BYTES = ROWS * KC * 2;   // 32 KB
+  // BMAX > 1 (tensor-core consumers): a stage is 8 weight rows x 2048 columns; rows of a stage / of the activation block are
+  // 64 bytes apart modulo 128, so the 16-byte fragment loads of a quarter-warp never share a bank
+  static constexpr int ROWS_TC = 8, KC_TC = 2048;
+  static constexpr int ROW_STRIDE_TC = KC_TC * 2 + 64;
+  static constexpr int STAGE_BYTES_TC = ROWS_TC * ROW_STRIDE_TC;
   static constexpr int CONSUMERS = 512, THREADS = 576;   // producer warp + 16 compute warps + 1 finalize warp
   static constexpr int RED_SLOTS = 4;
   static constexpr int MAX_STAGES = 6;
@@ -81,6 +86,13 @@ VLY_DEVINL float ldcg_bf16(const __nv_bfloat16* p) {
   asm volatile("ld.global.cg.u16 %0, [%1];\n" : "=h"(v) : "l"(p) : "memory");
   return __uint_as_float((uint32_t)v << 16);
 }
+// D[16x8] += A[16x16] * B[16x8], bf16 inputs, fp32 accumulate (legacy tensor path: plenty for an HBM-bound consumer)
+VLY_DEVINL void mma_m16n8k16_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 VLY_DEVINL uint32_t ld_acquire_u32(const unsigned int* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -101,14 +113,25 @@ VLY_DEVINL void grid_sync_consumers(unsigned int* counter, unsigned int target, 
 template <int BMAX>
 __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p) {
   using M = MegaCfg;
-  constexpr int NV = M::ROWS * BMAX;
+  constexpr bool kTC = BMAX > 1;                                                         // tensor-core consumers
+  constexpr int ROWS = kTC ? M::ROWS_TC : M::ROWS;                                       // weight rows per work unit
+  constexpr int KC = kTC ? M::KC_TC : M::KC;                                             // columns per ring stage
+  constexpr int NV = ROWS * BMAX;
+  constexpr int ROW_STRIDE = kTC ? M::ROW_STRIDE_TC : M::KC * 2;                         // bytes between rows of a ring stage
+  constexpr int STAGE_B = kTC ? M::STAGE_BYTES_TC : M::STAGE_BYTES;
   extern __shared__ uint8_t msm_raw[];
   uint8_t* msm = msm_raw + ((128u - (smem_u32(msm_raw) & 127u)) & 127u);
-  uint8_t* ring = msm;                                                                   // [n_stages][4][KC] bf16
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ring + (size_t)p.n_stages * M::STAGE_BYTES);   // [BMAX][Kmax]
-  uint8_t* tail = reinterpret_cast<uint8_t*>(xs) + (((size_t)BMAX * p.Kmax * 2 + 127) & ~size_t(127));
-  float* scratch = reinterpret_cast<float*>(tail);                                       // attention teams
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail + M::ATTN_SCRATCH);
+  uint8_t* ring = msm;                                                                   // [n_stages][4][ROW_STRIDE]
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ring + (size_t)p.n_stages * STAGE_B);   // [BMAX][xs_stride]
+  // activation rows: stride == Kmax for the CUDA-core path; == 64 bytes modulo 128 for the tensor-core path
+  const int xs_stride = kTC ? (((p.Kmax * 2 + 127) & ~127) + 64) / 2 : p.Kmax;
+  // the attention teams' scratch ALIASES the activation block: x is re-staged at the start of every weight phase and is
+  // dead during the attention phase (this keeps a third ring stage at 13B, B = 4 where x alone is 110 KB)
+  size_t xs_bytes = ((size_t)BMAX * xs_stride * 2 + 127) & ~size_t(127);
+  if (xs_bytes < (size_t)M::ATTN_SCRATCH) xs_bytes = M::ATTN_SCRATCH;
+  uint8_t* tail = reinterpret_cast<uint8_t*>(xs) + xs_bytes;
+  float* scratch = reinterpret_cast<float*>(xs);                                         // attention teams
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + M::MAX_STAGES;
   uint64_t* red_full = empty_bar + M::MAX_STAGES;                                        // [RED_SLOTS]
   uint64_t* red_empty = red_full + M::RED_SLOTS;                                         // [RED_SLOTS]
@@ -141,18 +164,18 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
       for (int pi = 0; pi < p.n_phases; ++pi) {
         const PhaseDesc& d = p.phases[pi];
         if (d.type == PH_ATTN) continue;
-        const int n_groups = (d.N + M::ROWS - 1) / M::ROWS;
-        const int n_slices = (d.K + M::KC - 1) / M::KC;
+        const int n_groups = (d.N + ROWS - 1) / ROWS;
+        const int n_slices = (d.K + KC - 1) / KC;
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-          const int n0 = g * M::ROWS;
-          const int rows = min(M::ROWS, d.N - n0);
+          const int n0 = g * ROWS;
+          const int rows = min(ROWS, d.N - n0);
           for (int s = 0; s < n_slices; ++s) {
-            const int kc = min(M::KC, d.K - s * M::KC);
+            const int kc = min(KC, d.K - s * KC);
             mbar_wait(&empty_bar[st], ph ^ 1);
             mbar_expect_tx(&full_bar[st], (uint32_t)rows * kc * 2);
-            uint8_t* dst = ring + (size_t)st * M::STAGE_BYTES;
-            const __nv_bfloat16* src = d.W + (size_t)n0 * d.K + (size_t)s * M::KC;
-            for (int r = 0; r < rows; ++r) bulk_load_1d(dst + r * (M::KC * 2), src + (size_t)r * d.K, (uint32_t)kc * 2, &full_bar[st]);
+            uint8_t* dst = ring + (size_t)st * STAGE_B;
+            const __nv_bfloat16* src = d.W + (size_t)n0 * d.K + (size_t)s * KC;
+            for (int r = 0; r < rows; ++r) bulk_load_1d(dst + r * ROW_STRIDE, src + (size_t)r * d.K, (uint32_t)kc * 2, &full_bar[st]);
             if (++st == p.n_stages) { st = 0; ph ^= 1; }
           }
         }
@@ -214,18 +237,27 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
             qf[0] = bf16_lo(w.x); qf[1] = bf16_hi(w.x); qf[2] = bf16_lo(w.y); qf[3] = bf16_hi(w.y);
             qf[4] = bf16_lo(w.z); qf[5] = bf16_hi(w.z); qf[6] = bf16_lo(w.w); qf[7] = bf16_hi(w.w);
           }
-          for (int i0 = tw * 2; i0 < nk; i0 += 8) {
-            const int i = i0 + (lane >> 4);
-            const bool ok = i < nk;
-            uint4 w = make_uint4(0, 0, 0, 0);
-            if (ok) w = ldcg_v4(kb + (size_t)(k0 + i) * 128 + hl * 8);
+          // every K and V row this thread needs is requested up front (one L2 round trip instead of 16 serialised ones):
+          // scores: half-warp per key, keys tw*2 + (lane>>4) + 8j;  P.V: 16 threads per key, keys (tt>>4) + 8j
+          uint4 kw[8], vw[8];
+          const int ki0 = tw * 2 + (lane >> 4), vi0 = tt >> 4, dl = tt & 15;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int ik = ki0 + 8 * j, iv = vi0 + 8 * j;
+            kw[j] = (ik < nk) ? ldcg_v4(kb + (size_t)(k0 + ik) * 128 + hl * 8) : make_uint4(0, 0, 0, 0);
+            vw[j] = (iv < nk) ? ldcg_v4(vb + (size_t)(k0 + iv) * 128 + dl * 8) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = ki0 + 8 * j;
+            const uint4 w = kw[j];
             float dd = qf[0] * bf16_lo(w.x) + qf[1] * bf16_hi(w.x) + qf[2] * bf16_lo(w.y) + qf[3] * bf16_hi(w.y) +
                        qf[4] * bf16_lo(w.z) + qf[5] * bf16_hi(w.z) + qf[6] * bf16_lo(w.w) + qf[7] * bf16_hi(w.w);
             dd += __shfl_xor_sync(0xffffffffu, dd, 8);
             dd += __shfl_xor_sync(0xffffffffu, dd, 4);
             dd += __shfl_xor_sync(0xffffffffu, dd, 2);
             dd += __shfl_xor_sync(0xffffffffu, dd, 1);
-            if (ok && hl == 0) sc[i] = dd * p.scale_log2e;
+            if (i < nk && hl == 0) sc[i] = dd * p.scale_log2e;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
           const float s0 = lane < nk ? sc[lane] : -INFINITY, s1 = lane + 32 < nk ? sc[lane + 32] : -INFINITY;
@@ -239,11 +271,13 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
           }
           asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
           {
-            const int g = tt >> 4, dl = tt & 15;
+            const int g = vi0;
             float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int i = g; i < nk; i += 8) {
-              const float pw = sc[i];
-              const uint4 w = ldcg_v4(vb + (size_t)(k0 + i) * 128 + dl * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int i = g + 8 * j;
+              const float pw = (i < nk) ? sc[i] : 0.f;
+              const uint4 w = vw[j];
               o[0] = fmaf(pw, bf16_lo(w.x), o[0]); o[1] = fmaf(pw, bf16_hi(w.x), o[1]);
               o[2] = fmaf(pw, bf16_lo(w.y), o[2]); o[3] = fmaf(pw, bf16_hi(w.y), o[3]);
               o[4] = fmaf(pw, bf16_lo(w.z), o[4]); o[5] = fmaf(pw, bf16_hi(w.z), o[5]);
@@ -293,7 +327,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
           for (int b = 0; b < BMAX; ++b) {
             uint4 w = make_uint4(0, 0, 0, 0);
             if (b < p.B) w = ldcg_v4(d.x_in + (size_t)b * d.K + c * 8);
-            *reinterpret_cast<uint4*>(xs + (size_t)b * p.Kmax + c * 8) = w;
+            *reinterpret_cast<uint4*>(xs + (size_t)b * xs_stride + c * 8) = w;
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -319,32 +353,72 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
       asm volatile("bar.sync 2, 544;" ::: "memory");
       t_stage += clock64() - t0;
       t0 = clock64();
-      const int n_groups = (d.N + M::ROWS - 1) / M::ROWS;
-      const int n_slices = (d.K + M::KC - 1) / M::KC;
+      const int n_groups = (d.N + ROWS - 1) / ROWS;
+      const int n_slices = (d.K + KC - 1) / KC;
       if (!is_fin) {
         // ===== compute warps: ring stage x activation rows -> per-warp partials -> handoff slot =====
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
-          const int n0 = g * M::ROWS;
-          const int rows = min(M::ROWS, d.N - n0);
+          const int n0 = g * ROWS;
+          const int rows = min(ROWS, d.N - n0);
+          const int slot = unit_no & (M::RED_SLOTS - 1);
+          const uint32_t round = (unit_no / M::RED_SLOTS) & 1;
+          if constexpr (kTC) {
+            // ---- tensor-core consumer (B = 2..4): mma.sync m16n8k16 with A = activation rows (batch on M, rows >= B zero)
+            // and B = 8 weight rows (N).  Lane (g = lane/4, t = lane%4) loads 16 contiguous bytes x[g][k..k+7] and
+            // W[g][k..k+7]; both operands use the same k permutation, so two MMAs consume them.
+            const int gq = lane >> 2, tq = lane & 3;
+            float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int s = 0; s < n_slices; ++s) {
+              const int kc = min(KC, d.K - s * KC);
+              mbar_wait(&full_bar[st], ph);
+              const uint8_t* wrow = ring + (size_t)st * STAGE_B + gq * ROW_STRIDE;
+              const __nv_bfloat16* xrow = xs + (size_t)gq * xs_stride + (size_t)s * KC;
+              const bool w_ok = gq < rows, x_ok = gq < p.B;
+#pragma unroll
+              for (int j = 0; j < KC / (16 * 32); ++j) {
+                const int k = cw * (KC / 16) + j * 32;       // this warp's 32-wide k block (warp-uniform bound check)
+                if (k < kc) {
+                  uint4 wb = make_uint4(0, 0, 0, 0), xa = make_uint4(0, 0, 0, 0);
+                  if (w_ok) wb = *reinterpret_cast<const uint4*>(wrow + (k + tq * 8) * 2);
+                  if (x_ok) xa = *reinterpret_cast<const uint4*>(xrow + k + tq * 8);
+                  mma_m16n8k16_bf16(dacc, xa.x, 0u, xa.y, 0u, wb.x, wb.y);
+                  mma_m16n8k16_bf16(dacc, xa.z, 0u, xa.w, 0u, wb.z, wb.w);
+                }
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty_bar[st]);
+              if (++st == p.n_stages) { st = 0; ph ^= 1; }
+            }
+            // lane (g < B, t) holds D[batch g][weight rows 2t, 2t+1] summed over this warp's k range
+            mbar_wait(&red_empty[slot], round ^ 1);
+            if (gq < BMAX) {
+              float* rp = red + (slot * 16 + cw) * NV;
+              rp[(2 * tq) * BMAX + gq] = dacc[0];
+              rp[(2 * tq + 1) * BMAX + gq] = dacc[1];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&red_full[slot]);
+            continue;
+          }
           float acc[NV];
 #pragma unroll
           for (int i = 0; i < NV; ++i) acc[i] = 0.f;
           for (int s = 0; s < n_slices; ++s) {
-            const int kc = min(M::KC, d.K - s * M::KC);
+            const int kc = min(KC, d.K - s * KC);
             mbar_wait(&full_bar[st], ph);
             if (ct * 8 < kc) {
-              const uint8_t* src = ring + (size_t)st * M::STAGE_BYTES + ct * 16;
+              const uint8_t* src = ring + (size_t)st * STAGE_B + ct * 16;
               float xf[BMAX][8];
 #pragma unroll
               for (int b = 0; b < BMAX; ++b) {
-                const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * p.Kmax + (size_t)s * M::KC + ct * 8);
+                const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * xs_stride + (size_t)s * KC + ct * 8);
                 xf[b][0] = bf16_lo(xv.x); xf[b][1] = bf16_hi(xv.x); xf[b][2] = bf16_lo(xv.y); xf[b][3] = bf16_hi(xv.y);
                 xf[b][4] = bf16_lo(xv.z); xf[b][5] = bf16_hi(xv.z); xf[b][6] = bf16_lo(xv.w); xf[b][7] = bf16_hi(xv.w);
               }
 #pragma unroll
-              for (int r = 0; r < M::ROWS; ++r) {
+              for (int r = 0; r < ROWS; ++r) {
                 if (r < rows) {
-                  const uint4 wv = *reinterpret_cast<const uint4*>(src + r * (M::KC * 2));
+                  const uint4 wv = *reinterpret_cast<const uint4*>(src + r * ROW_STRIDE);
                   const float wf[8] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y),
                                        bf16_lo(wv.z), bf16_hi(wv.z), bf16_lo(wv.w), bf16_hi(wv.w)};
 #pragma unroll
@@ -359,8 +433,6 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
             if (++st == p.n_stages) { st = 0; ph ^= 1; }
           }
           warp_reduce_scatter<NV>(acc, lane);
-          const int slot = unit_no & (M::RED_SLOTS - 1);
-          const uint32_t round = (unit_no / M::RED_SLOTS) & 1;
           mbar_wait(&red_empty[slot], round ^ 1);           // the finalize warp has drained this slot (4 units ago)
           if ((lane & (32 / NV - 1)) == 0) red[(slot * 16 + cw) * NV + lane / (32 / NV)] = acc[0];
           __syncwarp();
@@ -370,7 +442,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         // ===== finalize warp: sum the 16 partials of each unit, fused epilogue =====
         constexpr unsigned kMask = (NV == 32) ? 0xffffffffu : ((1u << NV) - 1u);
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
-          const int n0 = g * M::ROWS;
+          const int n0 = g * ROWS;
           const int slot = unit_no & (M::RED_SLOTS - 1);
           const uint32_t round = (unit_no / M::RED_SLOTS) & 1;
           const int r = lane / BMAX, b = lane % BMAX, n = n0 + r;
