@@ -260,6 +260,13 @@ static int launch_gemm(vly_ctx* c, int bn, const bf16* A, long long lda, const b
   return launch_gemm_t<128, EPI>(c, A, lda, W, ldw, p, st);
 }
 static inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
+// Small problems: a 128 x 256 tiling that covers less than ~2/3 of the SMs is re-tiled 128 x 128 (twice the CTAs, half the
+// main loop per CTA).  M-dependent, so callers that exchange row statistics compute it ONCE per (N, M) and pass it around.
+static inline int pick_bn_m(const vly_ctx* c, int N, int M) {
+  if (N % 256 != 0) return 128;
+  const int tiles256 = cdiv(M, 128) * (N / 256);
+  return (tiles256 * 3 < c->num_sms * 2) ? 128 : 256;
+}
 
 // ------------------------------------------------------------------------------------------------
 // weight packing kernels
@@ -719,12 +726,13 @@ static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int 
   TRY(ensure(c->w_qkv, Mmax * 3 * D * 2));
   TRY(ensure(c->w_ctx, Mmax * D * 2));
   TRY(ensure(c->w_h, Mmax * MLP * 2));
-  const int nt = cdiv(D, pick_bn(D));
-  TRY(ensure(c->w_stats, Mmax * nt * sizeof(float2)));
+  const int nt_max = cdiv(D, 128);
+  TRY(ensure(c->w_stats, Mmax * nt_max * sizeof(float2)));
   const size_t px_elem = pixel_dtype == VLY_F32 ? 4 : 2;
   for (int f0 = 0; f0 < F; f0 += CH) {
     const int fc = (F - f0) < CH ? (F - f0) : CH;
     const int M = fc * tokens;
+    const int bn_d = pick_bn_m(c, D, M), nt = cdiv(D, bn_d);       // every N = D GEMM of this chunk (they exchange row statistics)
     const char* px = (const char*)pixels + (size_t)f0 * 3 * IMG * IMG * px_elem;
     bf16* x = (bf16*)out_dev + (size_t)f0 * tokens * D;
     bf16* col = (bf16*)c->w_col.p;
@@ -739,7 +747,7 @@ static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int 
       GemmParams p = {};
       p.M = fc * NP; p.N = D; p.K = c->kpad;
       p.out = c->w_patch.p; p.ldo = D;
-      TRY(launch_gemm<EPI_BIAS>(c, pick_bn(D), col, c->kpad, c->patch_w, c->kpad, p, st));
+      TRY(launch_gemm<EPI_BIAS>(c, pick_bn_m(c, D, fc * NP), col, c->kpad, c->patch_w, c->kpad, p, st));
     }
     float2* stats = (float2*)c->w_stats.p;
     vit_embed_ln_kernel<<<M, 128, 0, st>>>((bf16*)c->w_patch.p, c->cls, c->pos, c->pre_g, c->pre_b, x, stats, nt, tokens, D, g.vit_eps);
@@ -753,21 +761,21 @@ static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int 
         p.out = c->w_qkv.p; p.ldo = 3 * D;
         p.bias = w.qkv_b; p.colsum = w.qkv_cs;
         p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / D; p.eps = g.vit_eps;
-        TRY(launch_gemm<EPI_LN_BIAS>(c, pick_bn(3 * D), x, D, w.wqkv, D, p, st));
+        TRY(launch_gemm<EPI_LN_BIAS>(c, pick_bn_m(c, 3 * D, M), x, D, w.wqkv, D, p, st));
       }
       TRY(launch_vit_attention(c, (bf16*)c->w_qkv.p, fc, (bf16*)c->w_ctx.p, st));
       {  // out_proj + residual
         GemmParams p = {};
         p.M = M; p.N = D; p.K = D;
         p.out = x; p.ldo = D; p.bias = w.bo; p.residual = x; p.ldr = D; p.stats_out = stats;
-        TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, pick_bn(D), (bf16*)c->w_ctx.p, D, w.wo, D, p, st));
+        TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, bn_d, (bf16*)c->w_ctx.p, D, w.wo, D, p, st));
       }
       {  // LN2 -> fc1 -> quick_gelu
         GemmParams p = {};
         p.M = M; p.N = MLP; p.K = D;
         p.out = c->w_h.p; p.ldo = MLP; p.bias = w.b1; p.colsum = w.c1;
         p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / D; p.eps = g.vit_eps;
-        TRY(launch_gemm<EPI_LN_BIAS_GELU>(c, pick_bn(MLP), x, D, w.w1, D, p, st));
+        TRY(launch_gemm<EPI_LN_BIAS_GELU>(c, pick_bn_m(c, MLP, M), x, D, w.w1, D, p, st));
       }
       {  // fc2 + residual (+ on the last layer of a sharded encode: push every tile to all ranks' gather buffers)
         GemmParams p = {};
@@ -778,7 +786,7 @@ static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int 
           for (int q = 0; q < c->g_world; ++q) p.peer_out[q] = c->g_peer_buf[q];
           p.peer_row_off = gather_row_off + (long long)f0 * tokens;
         }
-        TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, pick_bn(D), (bf16*)c->w_h.p, MLP, w.w2, MLP, p, st));
+        TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, bn_d, (bf16*)c->w_h.p, MLP, w.w2, MLP, p, st));
       }
     }
     if (gather && n_layers == 0) return fail(VLY_ERR_INVALID, "vly_vit_encode_gather needs at least one encoder layer (select_layer != 0)");
@@ -1247,7 +1255,7 @@ extern "C" int vly_llama_prefill(vly_ctx* c, vly_kv* kv, const void* inputs_embe
   const vly_config& g = c->cfg;
   const int H = g.hidden_size, nH = g.num_attention_heads, I = g.intermediate_size, V = g.vocab_size;
   const int M = B * S;
-  const int bn_h = pick_bn(H), nt = cdiv(H, bn_h);
+  const int bn_h = pick_bn_m(c, H, M), nt = cdiv(H, bn_h);
   TRY(ensure(c->w_x, (size_t)M * H * 2));
   TRY(ensure(c->w_q, (size_t)M * H * 2));
   TRY(ensure(c->w_attn, (size_t)M * H * 2));
@@ -1266,7 +1274,7 @@ extern "C" int vly_llama_prefill(vly_ctx* c, vly_kv* kv, const void* inputs_embe
       p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / H; p.eps = g.rms_norm_eps;
       p.rope = c->rope; p.S = S; p.past = past; p.H = H; p.nH = nH; p.Smax = kv->Smax;
       p.kcache = kv->k_layer(l); p.vcache = kv->v_layer(l);
-      TRY(launch_gemm<EPI_RMS_QKV_ROPE>(c, pick_bn(3 * H), x, H, w.wqkv, H, p, st));
+      TRY(launch_gemm<EPI_RMS_QKV_ROPE>(c, pick_bn_m(c, 3 * H, M), x, H, w.wqkv, H, p, st));
     }
     TRY(launch_prefill_attention(c, kv, qb, B, S, past, l, attn, st));
     {
@@ -1278,7 +1286,7 @@ extern "C" int vly_llama_prefill(vly_ctx* c, vly_kv* kv, const void* inputs_embe
       GemmParams p = {};
       p.M = M; p.N = 2 * I; p.K = H; p.out = hb; p.ldo = I;
       p.stats_in = stats; p.stats_in_nt = nt; p.inv_dim = 1.f / H; p.eps = g.rms_norm_eps;
-      TRY(launch_gemm<EPI_RMS_SWIGLU>(c, pick_bn(2 * I), x, H, w.wgu, H, p, st));
+      TRY(launch_gemm<EPI_RMS_SWIGLU>(c, pick_bn_m(c, 2 * I, M), x, H, w.wgu, H, p, st));
     }
     {
       GemmParams p = {};
