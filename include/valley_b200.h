@@ -121,6 +121,12 @@ int vly_kv_create(vly_ctx* ctx, int batch, int max_seq, vly_kv** out);
 void vly_kv_destroy(vly_kv* kv);
 int vly_kv_seq_len(vly_kv* kv, int* out_len);   /* host-visible length (syncs the kv's stream state) */
 int vly_kv_reset(vly_kv* kv, void* stream);
+/* HF's 2-D attention_mask (HF masking_utils: the padding mask is AND-ed into the causal mask; build_inputs /
+ * tokenizer(padding=True) pad on the LEFT, valley_model.py:249-254 passes the mask through): mask_dev [B, len] uint8 on the
+ * device, 0 = cache position k of sequence b must never be attended.  Covers cache positions [0, len) -- set it before the
+ * prefill that appends them; later positions (decode) are attendable.  Position ids are NOT shifted by padding (the
+ * reference never passes position_ids).  len = 0 clears the mask; vly_kv_reset clears it too. */
+int vly_kv_set_key_mask(vly_kv* kv, const uint8_t* mask_dev, int len, void* stream);
 /* copy layer l's K (which=0) or V (which=1) as HF-layout [B,heads,len,128] bf16 (de-interleaves K) -- for tests/drop-in */
 int vly_kv_export(vly_ctx* ctx, vly_kv* kv, int layer, int which, void* out_dev, void* stream);
 

@@ -136,6 +136,30 @@ def main():
             assert torch.equal(o_tok, r_tok), "greedy token ids differ"
             print("  greedy token ids identical:", r_tok[0].tolist())
 
+            # --- left-padded batch with a 2-D attention_mask (build_inputs pads left; HF masks the padded keys,
+            #     positions are NOT shifted): prefill + 3 cached decode steps, compared at the non-pad positions -----
+            pad = 5
+            ids_p = torch.cat([ids[:, :pad], ids], 1)
+            am = torch.ones_like(ids_p)
+            am[0, :pad] = 0
+            ids_p[0, :pad] = 0
+            lp_out = ref(ids_p, attention_mask=am, images=px, use_cache=True)
+            lp_cache = O.KVCache(spec.num_hidden_layers)
+            mine = O.causal_lm_forward(sd, cfg, tok, ids_p, px, lp_cache, attention_mask=am)
+            close(mine[am.bool()], lp_out.logits[am.bool()], "left-pad prefill logits (non-pad rows)")
+            lp_steps, lp_mask, past = [], am, lp_out.past_key_values
+            cur = lp_out.logits[:, -1].argmax(-1)[:, None]
+            lp_first = cur.clone()
+            for i in range(3):
+                lp_mask = torch.cat([lp_mask, torch.ones(B, 1, dtype=am.dtype)], 1)
+                o = ref(input_ids=cur, attention_mask=lp_mask, past_key_values=past, use_cache=True)
+                mo = O.causal_lm_forward(sd, cfg, tok, cur, None, lp_cache, attention_mask=lp_mask)
+                close(mo, o.logits, f"left-pad decode step {i} logits")
+                lp_steps.append(o.logits[:, -1].clone())
+                cur = o.logits[:, -1].argmax(-1)[:, None]
+            gold_leftpad = dict(ids=ids_p, mask=am, prefill_logits_last=lp_out.logits[:, -1].clone(), first_token=lp_first,
+                                decode_logits=torch.stack(lp_steps, 1))
+
             # --- inputs_embeds after splice: hook the reference's LlamaModel.forward -----------
             grabbed = {}
             import transformers
@@ -198,7 +222,7 @@ def main():
                 spec=spec.name, seed=seed, B=B, T=T,
                 vit_hidden_m2_sub=hs[-2][:, ::4, ::8].clone(), vit_hidden_m1_sub=hs[-1][:, ::4, ::8].clone(),
                 prefill_logits_last=out.logits[:, -1, :].clone(), prefill_logits_sub=out.logits[:, ::16, ::8].clone(),
-                greedy_tokens=r_tok, greedy_logits=r_log, splice=gold_splice, errors=errs,
+                greedy_tokens=r_tok, greedy_logits=r_log, splice=gold_splice, errors=errs, leftpad=gold_leftpad,
             ), os.path.join(GOLD, f"ref_{spec.name}.pt"))
             print("  wrote", f"tests/golden/ref_{spec.name}.pt")
     print("oracle == reference on all cases; golden fixtures written")

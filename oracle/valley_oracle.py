@@ -245,19 +245,22 @@ def llama_layer(w: Dict[str, Tensor], x: Tensor, pfx: str, cos: Tensor, sin: Ten
 
 
 def llama_model(w: Dict[str, Tensor], inputs_embeds: Tensor, cache: Optional[KVCache], *, n_layers: int,
-                heads: int, eps: float, theta: float = 10000.0) -> Tensor:
+                heads: int, eps: float, theta: float = 10000.0, attention_mask: Optional[Tensor] = None) -> Tensor:
     """HF:modeling_llama.py:375-426 (LlamaModel.forward) with Valley's call (valley_model.py:249-254):
-    position_ids = cache_len + arange(S) (never passed by Valley, Appendix A.8), causal mask,
-    L decoder layers, final RMSNorm."""
+    position_ids = cache_len + arange(S) (never passed by Valley, Appendix A.8) -- NOT shifted by padding --, causal
+    mask AND-ed with the 2-D ``attention_mask`` [B, past+S] over keys (HF masking_utils: padding mask), L decoder
+    layers, final RMSNorm."""
     B, S, H = inputs_embeds.shape
     past = cache.get_seq_length() if cache is not None else 0
     pos = (past + torch.arange(S))[None, :].expand(B, -1)
     cos, sin = rope_cos_sin(pos, H // heads, theta, inputs_embeds.dtype)
     mask = None
-    if S > 1:
+    if S > 1 or attention_mask is not None:
         neg = torch.finfo(inputs_embeds.dtype).min
-        allowed = torch.arange(past + S)[None, :] <= (past + torch.arange(S))[:, None]
-        mask = torch.zeros(S, past + S, dtype=inputs_embeds.dtype).masked_fill(~allowed, neg)[None, None]
+        allowed = (torch.arange(past + S)[None, :] <= (past + torch.arange(S))[:, None])[None]      # [1,S,past+S]
+        if attention_mask is not None:
+            allowed = allowed & attention_mask[:, None, : past + S].bool()                            # [B,S,past+S]
+        mask = torch.zeros(allowed.shape, dtype=inputs_embeds.dtype).masked_fill(~allowed, neg)[:, None]
     x = inputs_embeds
     for i in range(n_layers):
         x = llama_layer(w, x, f"model.layers.{i}.", cos, sin, mask, cache, i, heads, eps)
@@ -279,7 +282,7 @@ class OracleConfig:
 
 
 def causal_lm_forward(w: Dict[str, Tensor], cfg: OracleConfig, tok: SentinelIds, input_ids: Tensor,
-                      images=None, cache: Optional[KVCache] = None) -> Tensor:
+                      images=None, cache: Optional[KVCache] = None, attention_mask: Optional[Tensor] = None) -> Tensor:
     """ValleyLlamaForCausalLM.forward (valley_model.py:272-330) -> logits [B,S,V].
     Vision runs only when input_ids.shape[1] != 1 and images is not None (:163-164)."""
     if images is not None and input_ids.shape[1] != 1:
@@ -289,21 +292,24 @@ def causal_lm_forward(w: Dict[str, Tensor], cfg: OracleConfig, tok: SentinelIds,
     else:
         embeds = F.embedding(input_ids, w["model.embed_tokens.weight"])
     hidden = llama_model(w, embeds, cache, n_layers=cfg.num_hidden_layers, heads=cfg.num_attention_heads,
-                         eps=cfg.rms_norm_eps, theta=cfg.rope_theta)
+                         eps=cfg.rms_norm_eps, theta=cfg.rope_theta, attention_mask=attention_mask)
     return F.linear(hidden, w["lm_head.weight"])                          # :304-305 (all positions)
 
 
 @torch.no_grad()
 def greedy_generate(w: Dict[str, Tensor], cfg: OracleConfig, tok: SentinelIds, input_ids: Tensor, images,
-                    max_new_tokens: int, return_logits: bool = False):
+                    max_new_tokens: int, return_logits: bool = False, attention_mask: Optional[Tensor] = None):
     """The reference's own explicit decode loop, valley/serve/model_worker.py:371-397 with
     temperature < 1e-4 (argmax, :390-391), generalised from B=1 to B rows.  Step 0 = prefill
-    with images; later steps feed the single new token with the cache."""
+    with images; later steps feed the single new token with the cache.  ``attention_mask`` [B, S] (left padding)
+    is extended by a column of ones per generated token (model_worker.py:382-383; HF generate does the same)."""
     cache = KVCache(cfg.num_hidden_layers)
     tokens, all_logits = [], []
     cur = input_ids
     for i in range(max_new_tokens):
-        logits = causal_lm_forward(w, cfg, tok, cur, images if i == 0 else None, cache)
+        if attention_mask is not None and i > 0:
+            attention_mask = torch.cat([attention_mask, torch.ones_like(attention_mask[:, :1])], dim=1)
+        logits = causal_lm_forward(w, cfg, tok, cur, images if i == 0 else None, cache, attention_mask=attention_mask)
         last = logits[:, -1, :]
         nxt = torch.argmax(last, dim=-1)
         tokens.append(nxt)

@@ -233,6 +233,72 @@ def test_generate_host_loop_equals_device_loop_and_stops():
     assert inp["input_ids"].shape == a.shape and inp["images"] is px
 
 
+@pytest.mark.parametrize("B,pads", [(2, (5, 0)), (1, (3,)), (3, (0, 130, 64)), (6, (0, 130, 1, 64, 7, 0))])
+def test_left_padded_batch_vs_oracle(B, pads):
+    """attention_mask with LEFT padding (build_inputs / tokenizer(padding=True), valley_model.py:402-403): padded keys are never
+    attended, positions are not shifted.  Pads of 64 / 130 mask whole 64-key decode splits and a whole 128-key prefill tile.
+    B = 1, 2, 3 run the persistent decode kernel (CUDA-core and tensor-core consumers), B = 6 the grouped per-op kernels."""
+    spec, sd, m = get("tiny")
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    T, n, P = 3, 6, max(pads)
+    base, px = syn.make_prompt_ids(spec, B, T, 0), syn.make_pixels(B, T, 0)
+    fill = torch.randint(3, spec.vocab_size - 8, (B, P), generator=torch.Generator().manual_seed(3))
+    ids, am = torch.cat([fill, base], 1), torch.ones(B, P + base.shape[1], dtype=torch.int64)
+    for b, p in enumerate(pads):
+        ids[b, :p] = 0
+        am[b, :p] = 0
+    with torch.no_grad():
+        r_tok, r_log = O.greedy_generate(sd, cfg, tok, ids, px, n, return_logits=True, attention_mask=am)
+        u_log = O.causal_lm_forward(sd, cfg, tok, ids, px, None)[:, -1]      # the same batch with the mask ignored
+    out = m(input_ids=ids.cuda(), attention_mask=am.cuda(), images=px.cuda())      # logits at every position
+    assert torch.isfinite(out.logits).all()                     # fully masked (padding) query rows stay finite
+    cache, logs, mask = out.past_key_values, [out.logits[:, -1].cpu()], am
+    for b, p in enumerate(pads):     # every padded row must sit clearly on the masked side (a short pad moves logits by only ~1e-2)
+        if p:
+            assert Hh.rel_fro(logs[0][b], r_log[b, 0]) < 0.5 * Hh.rel_fro(logs[0][b], u_log[b]), (b, p)
+    for i in range(1, n):
+        mask = torch.cat([mask, torch.ones(B, 1, dtype=mask.dtype)], 1)
+        o = m(input_ids=r_tok[:, i - 1:i].cuda(), past_key_values=cache, attention_mask=mask)     # CPU mask on purpose
+        logs.append(o.logits[:, -1].cpu())
+    logs = torch.stack(logs, 1)
+    max_err = (logs - r_log).abs().max().item()
+    assert Hh.rel_fro(logs, r_log) < 2e-2, Hh.rel_fro(logs, r_log)
+    top2 = r_log.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * max_err
+    assert torch.equal(logs.argmax(-1)[safe], r_tok[safe])
+    gen = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n, attention_mask=am.cuda())[:, ids.shape[1]:].cpu()
+    for b in range(B):
+        for i in range(n):
+            if not safe[b, i]:
+                break
+            assert gen[b, i] == r_tok[b, i], (b, i)
+    # a recycled cache must not remember the mask: the same unpadded request before and after gives the same ids
+    plain = m.generate(input_ids=base.cuda(), images=px.cuda(), max_new_tokens=n)
+    fresh = m._generate_with_cache(m.new_cache(B), base, m.prepare_inputs_labels_for_multimodal(base, None, None, None, px)[3],
+                                   n, False, 1.0, None, None)
+    assert torch.equal(plain, fresh)
+    with pytest.raises(ValueError):
+        m(input_ids=ids.cuda(), attention_mask=am[:, :-1].cuda(), images=px.cuda())
+
+
+def test_left_padded_golden_reference_logits():
+    """The REFERENCE's own fp32 outputs for a left-padded batch (tests/golden, oracle/make_golden.py)."""
+    g = torch.load(os.path.join(GOLD, "ref_tiny.pt"))
+    lp = g["leftpad"]
+    spec = syn.SPECS["tiny"]
+    sd = syn.make_state_dict(spec, g["seed"])
+    m = Hh.build_model(spec, sd)
+    px = syn.make_pixels(g["B"], g["T"], g["seed"])
+    out = m(input_ids=lp["ids"].cuda(), attention_mask=lp["mask"].cuda(), images=px.cuda())
+    assert Hh.rel_fro(out.logits[:, -1], lp["prefill_logits_last"]) < 2e-2
+    cache, cur, mask = out.past_key_values, lp["first_token"], lp["mask"]
+    for i in range(lp["decode_logits"].shape[1]):
+        mask = torch.cat([mask, torch.ones(mask.shape[0], 1, dtype=mask.dtype)], 1)
+        o = m(input_ids=cur.cuda(), past_key_values=cache, attention_mask=mask.cuda())
+        assert Hh.rel_fro(o.logits[:, -1], lp["decode_logits"][:, i]) < 2e-2
+        cur = lp["decode_logits"][:, i].argmax(-1)[:, None]
+
+
 def test_cache_capacity_is_enforced():
     spec, sd, m = get("tiny")
     ids = syn.make_prompt_ids(spec, 1, 2, 0)
@@ -240,3 +306,34 @@ def test_cache_capacity_is_enforced():
     m(input_ids=ids.cuda(), past_key_values=cache)
     with pytest.raises(ValueError):
         m(input_ids=ids.cuda(), past_key_values=cache)            # 2 x 327 > 384
+
+
+@pytest.mark.parametrize("spec_name,B", [("shape-13b-1l", 1), ("shape-13b-1l", 4), ("shape-7b-1l", 3)])
+def test_production_shapes_one_layer(spec_name, B):
+    """One decoder layer at the real 7B / 13B widths (H 4096/5120, I 11008/13824, 32/40 heads, V 32008): prefill logits and
+    6 teacher-forced decode steps vs the oracle -- covers the K-tail slices of the CUDA-core (B = 1) and tensor-core (B > 1)
+    decode consumers and the 256-wide / CTA-pair GEMM tilings."""
+    spec = syn.SPECS[spec_name]
+    sd = Hh.bf16_weights(spec, 2)
+    m = Hh.build_model(spec, sd)
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    T, n = 2, 6
+    ids, px = syn.make_prompt_ids(spec, B, T, 0, len_a=12, len_b=7), syn.make_pixels(B, T, 0)
+    with torch.no_grad():
+        r_tok, r_log = O.greedy_generate(sd, cfg, tok, ids, px, n, return_logits=True)
+    m.logits_all_positions = False
+    out = m(input_ids=ids.cuda(), images=px.cuda())
+    cache, logs = out.past_key_values, [out.logits[:, -1].cpu()]
+    for i in range(1, n):
+        o = m(input_ids=r_tok[:, i - 1:i].cuda(), past_key_values=cache)
+        logs.append(o.logits[:, -1].cpu())
+    logs = torch.stack(logs, 1)
+    assert not torch.isnan(logs).any()
+    assert Hh.rel_fro(logs, r_log) < 2e-2
+    max_err = (logs - r_log).abs().max().item()
+    top2 = r_log.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * max_err
+    assert torch.equal(logs.argmax(-1)[safe], r_tok[safe])
+    del m
+    _models.pop((spec_name, 2), None)
+    torch.cuda.empty_cache()

@@ -50,3 +50,24 @@ def test_oracle_splice_cases_match_reference(name):
             with pytest.raises(ValueError) as ei:
                 O.causal_lm_forward(sd, cfg, tok, d["ids"], px[:1], None)
             assert str(ei.value) == d["message"], case
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny-wide"])
+def test_oracle_left_padded_batch_matches_reference(name):
+    """attention_mask with left padding (model_worker/build_inputs pad left): masked keys, unshifted positions."""
+    g = torch.load(os.path.join(GOLD, f"ref_{name}.pt"))
+    spec, lp = syn.SPECS[name], g["leftpad"]
+    sd = syn.make_state_dict(spec, g["seed"])
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    px = syn.make_pixels(g["B"], g["T"], g["seed"])
+    with torch.no_grad():
+        cache = O.KVCache(spec.num_hidden_layers)
+        logits = O.causal_lm_forward(sd, cfg, tok, lp["ids"], px, cache, attention_mask=lp["mask"])
+        assert torch.allclose(logits[:, -1], lp["prefill_logits_last"], rtol=1e-4, atol=1e-5)
+        cur, mask = logits[:, -1].argmax(-1)[:, None], lp["mask"]
+        assert torch.equal(cur, lp["first_token"])
+        for i in range(lp["decode_logits"].shape[1]):
+            mask = torch.cat([mask, torch.ones(mask.shape[0], 1, dtype=mask.dtype)], 1)
+            lg = O.causal_lm_forward(sd, cfg, tok, cur, None, cache, attention_mask=mask)[:, -1]
+            assert torch.allclose(lg, lp["decode_logits"][:, i], rtol=1e-4, atol=1e-5)
+            cur = lg.argmax(-1)[:, None]

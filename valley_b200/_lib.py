@@ -57,6 +57,7 @@ SIGNATURES = {
     "vly_kv_destroy": (None, [_vp]),
     "vly_kv_seq_len": (_i, [_vp, _p(_i)]),
     "vly_kv_reset": (_i, [_vp, _vp]),
+    "vly_kv_set_key_mask": (_i, [_vp, _vp, _i, _vp]),
     "vly_kv_export": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "vly_llama_prefill": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "vly_llama_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

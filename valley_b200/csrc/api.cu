@@ -144,6 +144,9 @@ struct vly_kv {
   int n_phases = 0;
   unsigned int* grid_counter = nullptr;
   long long* dbg = nullptr;
+  uint32_t* key_bits = nullptr;       // [B, Smax/32] attention_mask bits (1 = attend); all ones unless vly_kv_set_key_mask
+  bool masked = false;
+  int mask_words() const { return Smax / 32; }
   cudaGraphExec_t graph = nullptr;
   int graph_nodes = 0;
   size_t layer_stride() const { return (size_t)2 * B * ctx->cfg.num_attention_heads * Smax * 128; }
@@ -986,6 +989,8 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   CK(cudaMalloc((void**)&kv->cur_tokens, (size_t)batch * 8));
   CK(cudaMalloc((void**)&kv->gen_tokens, (size_t)batch * kv->Smax * 8));
   CK(cudaMalloc((void**)&kv->dbg, 1024 * 8 * 8));
+  CK(cudaMalloc((void**)&kv->key_bits, (size_t)batch * kv->mask_words() * 4));
+  CK(cudaMemset(kv->key_bits, 0xff, (size_t)batch * kv->mask_words() * 4));
   {  // phase table of the persistent decode-step kernel: execution order of one step
     std::vector<PhaseDesc> ph;
     for (int l = 0; l < L; ++l) {
@@ -1012,7 +1017,7 @@ extern "C" void vly_kv_destroy(vly_kv* kv) {
   if (!kv) return;
   cudaSetDevice(kv->ctx->cfg.device);
   if (kv->graph) cudaGraphExecDestroy(kv->graph);
-  void* ps[] = {kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
+  void* ps[] = {kv->key_bits, kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
   for (void* p : ps)
     if (p) cudaFree(p);
   delete kv;
@@ -1029,6 +1034,38 @@ extern "C" int vly_kv_reset(vly_kv* kv, void* stream) {
   CK(cudaSetDevice(kv->ctx->cfg.device));
   kv->host_len = 0;
   CK(cudaMemsetAsync(kv->d_len, 0, 8, (cudaStream_t)stream));
+  if (kv->masked) {
+    CK(cudaMemsetAsync(kv->key_bits, 0xff, (size_t)kv->B * kv->mask_words() * 4, (cudaStream_t)stream));
+    kv->masked = false;
+  }
+  return VLY_OK;
+}
+
+// one thread per 32-key word: bit i = mask[b, 32w+i] != 0; positions >= len stay attendable
+__global__ void pack_key_mask_kernel(const uint8_t* __restrict__ mask, int len, int words, uint32_t* __restrict__ bits) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (w >= words) return;
+  uint32_t v = 0;
+  for (int i = 0; i < 32; ++i) {
+    const int k = w * 32 + i;
+    v |= uint32_t(k >= len || mask[(size_t)b * len + k] != 0) << i;
+  }
+  bits[(size_t)b * words + w] = v;
+}
+
+extern "C" int vly_kv_set_key_mask(vly_kv* kv, const uint8_t* mask_dev, int len, void* stream) {
+  if (!kv || len < 0 || len > kv->Smax || (len > 0 && !mask_dev)) return fail(VLY_ERR_INVALID, "vly_kv_set_key_mask: bad argument (len %d, capacity %d)", len, kv ? kv->Smax : 0);
+  CK(cudaSetDevice(kv->ctx->cfg.device));
+  const int words = kv->mask_words();
+  if (len == 0) {
+    CK(cudaMemsetAsync(kv->key_bits, 0xff, (size_t)kv->B * words * 4, (cudaStream_t)stream));
+    kv->masked = false;
+    return VLY_OK;
+  }
+  pack_key_mask_kernel<<<dim3(cdiv(words, 128), kv->B), 128, 0, (cudaStream_t)stream>>>(mask_dev, len, words, kv->key_bits);
+  kv->ctx->launches++;
+  CKL();
+  kv->masked = true;
   return VLY_OK;
 }
 
@@ -1163,6 +1200,7 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
       p.counters = kv->counters + (size_t)b0 * nH;
       p.out = attn;
       p.scale_log2e = 0.08838834764831845f * 1.4426950408889634f;
+      p.key_bits = kv->key_bits + (size_t)b0 * kv->mask_words(); p.mask_words = kv->mask_words();
       if (use_decode_v1()) {
         dim3 grid(nb * nH, kv->nsplit);
         decode_attention_kernel<<<grid, 128, attn_smem, st>>>(p);
@@ -1234,6 +1272,7 @@ static int launch_prefill_attention(vly_ctx* c, vly_kv* kv, const bf16* qbuf, in
   PrefillAttnParams p;
   p.B = B; p.S = S; p.past = past; p.nH = nH; p.H = H; p.Smax = kv->Smax; p.ctx = out;
   p.scale_log2e = 0.08838834764831845f * 1.4426950408889634f;
+  p.key_bits = kv->masked ? kv->key_bits : nullptr; p.mask_words = kv->mask_words();
   const int n_qt = cdiv(S, 128);
   llama_prefill_attention_kernel<<<B * nH * n_qt, PrefillAttnCfg::THREADS, PrefillAttnCfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
   c->launches++;
@@ -1344,6 +1383,7 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   p.rope = c->rope; p.seq_len = kv->d_len; p.step = kv->d_step; p.embed = c->embed; p.tokens_in = kv->cur_tokens;
   p.x = kv->x; p.q = kv->q; p.attn = kv->attn;
   p.part_o = kv->part_o; p.part_ml = kv->part_ml; p.attn_counters = kv->counters; p.nsplit = kv->nsplit;
+  p.key_bits = kv->key_bits; p.mask_words = kv->mask_words();
   p.logits = kv->logits; p.part_val = kv->part_val; p.part_idx = kv->part_idx;
   p.next_tokens = kv->cur_tokens; p.out_tokens = kv->gen_tokens; p.out_stride = kv->Smax;
   p.grid_counter = kv->grid_counter;

@@ -298,6 +298,10 @@ struct PrefillAttnParams {
   int B, S, past, nH, H, Smax;
   __nv_bfloat16* ctx;   // [B*S, H]
   float scale_log2e;    // 128^-0.5 * log2(e)
+  // HF's 2-D attention_mask (padding mask AND-ed into the causal mask, HF:masking_utils), one bit per cache position:
+  // [B, mask_words] words, bit k of row b = key k may be attended.  NULL = no key is masked (the common case).
+  const uint32_t* key_bits;
+  int mask_words;
 };
 
 struct PrefillAttnCfg {
@@ -446,6 +450,7 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
     const int q_pos = p.past + q_idx;         // absolute position
     uint32_t sf_ph = 0, pe_ph = 0;
     float m = -INFINITY, l = 0.f;
+    const uint32_t* kbits = p.key_bits ? p.key_bits + (size_t)b * p.mask_words : nullptr;
     // ---------------- pass 1: running max / sum ----------------
     for (int j = 0; j < nkv; ++j) {
       __syncwarp();
@@ -457,11 +462,12 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + lane_addr + c * 32, v);
         tmem_ld_wait();
+        const uint32_t kb = kbits ? __ldg(kbits + j * 4 + c) : 0xffffffffu;
         float s[32], cm = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int key = j * 128 + c * 32 + i;
-          s[i] = (key <= q_pos && key < kv_len) ? __uint_as_float(v[i]) * p.scale_log2e : -INFINITY;
+          s[i] = (key <= q_pos && key < kv_len && ((kb >> i) & 1u)) ? __uint_as_float(v[i]) * p.scale_log2e : -INFINITY;
           cm = fmaxf(cm, s[i]);
         }
         const float mn = fmaxf(m, cm);
@@ -491,11 +497,13 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + lane_addr + c * 32, v);
         tmem_ld_wait();
+        // a row whose every visible key is masked (a left-padding query) keeps m = -inf: kb is forced to 0 there, so e = 0
+        const uint32_t kb = m > -INFINITY ? (kbits ? __ldg(kbits + j * 4 + c) : 0xffffffffu) : 0u;
         float e[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int key = j * 128 + c * 32 + i;
-          e[i] = (key <= q_pos && key < kv_len) ? fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, -m)) : 0.f;
+          e[i] = (key <= q_pos && key < kv_len && ((kb >> i) & 1u)) ? fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, -m)) : 0.f;
         }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
@@ -513,7 +521,7 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
     __syncwarp();
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv = __frcp_rn(l);
+    const float inv = l > 0.f ? __frcp_rn(l) : 0.f;     // fully masked query row -> zeros (its output is never attended)
     __nv_bfloat16* dst = p.ctx + ((size_t)b * p.S + q_idx) * p.H + h * 128;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {

@@ -353,13 +353,13 @@ __global__ void __launch_bounds__(128) decode_attention_v2_kernel(const DecAttnP
       d += __shfl_xor_sync(0xffffffffu, d, 4);
       d += __shfl_xor_sync(0xffffffffu, d, 2);
       d += __shfl_xor_sync(0xffffffffu, d, 1);
-      if (ok && hl == 0) sc[i] = d * p.scale_log2e;
+      if (ok && hl == 0) sc[i] = key_attendable(p.key_bits + (size_t)b * p.mask_words, k0 + i) ? d * p.scale_log2e : -INFINITY;
     }
     __syncthreads();
     // 64 scores: every warp redundantly reduces them (no extra block barriers)
     const float s0 = lane < nk ? sc[lane] : -INFINITY, s1 = lane + 32 < nk ? sc[lane + 32] : -INFINITY;
     m = warp_max(fmaxf(s0, s1));
-    const float e0 = lane < nk ? fast_exp2(s0 - m) : 0.f, e1 = lane + 32 < nk ? fast_exp2(s1 - m) : 0.f;
+    const float e0 = s0 > -INFINITY ? fast_exp2(s0 - m) : 0.f, e1 = s1 > -INFINITY ? fast_exp2(s1 - m) : 0.f;
     l = warp_sum(e0 + e1);
     __syncthreads();
     if (warp == 0) {
@@ -400,11 +400,11 @@ __global__ void __launch_bounds__(128) decode_attention_v2_kernel(const DecAttnP
     for (int s = 0; s < n_act; ++s) {
       const float ms = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x);
       const float ls = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].y);
-      const float w = fast_exp2(ms - M);
+      const float w = ls > 0.f ? fast_exp2(ms - M) : 0.f;    // a fully masked split has m = -inf, l = 0
       L += ls * w;
       acc += __ldcg(p.part_o + ((size_t)bh * p.nsplit + s) * 128 + tid) * w;
     }
-    p.out[(size_t)b * p.H + h * 128 + tid] = __float2bfloat16_rn(acc / L);
+    p.out[(size_t)b * p.H + h * 128 + tid] = __float2bfloat16_rn(L > 0.f ? acc / L : 0.f);
     if (tid == 0) p.counters[bh] = 0;
   }
 }

@@ -51,6 +51,8 @@ struct StepParams {
   float2* part_ml;              // [B*nH, nsplit]
   unsigned int* attn_counters;  // [B*nH]
   int nsplit;
+  const uint32_t* key_bits;     // [B, mask_words] attention_mask, one bit per cache position (1 = attend)
+  int mask_words;
   float* logits;                // [B, V]
   float* part_val;              // [B, grid]
   int* part_idx;
@@ -260,9 +262,12 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
             if (i < nk && hl == 0) sc[i] = dd * p.scale_log2e;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-          const float s0 = lane < nk ? sc[lane] : -INFINITY, s1 = lane + 32 < nk ? sc[lane + 32] : -INFINITY;
+          // attention_mask: one bit per cache position, two words per 64-key split (all ones unless the caller masked keys)
+          const uint2 kbits = __ldg(reinterpret_cast<const uint2*>(p.key_bits + (size_t)b * p.mask_words + (k0 >> 5)));
+          const float s0 = (lane < nk && ((kbits.x >> lane) & 1u)) ? sc[lane] : -INFINITY;
+          const float s1 = (lane + 32 < nk && ((kbits.y >> lane) & 1u)) ? sc[lane + 32] : -INFINITY;
           const float mx = warp_max(fmaxf(s0, s1));
-          const float e0 = lane < nk ? fast_exp2(s0 - mx) : 0.f, e1 = lane + 32 < nk ? fast_exp2(s1 - mx) : 0.f;
+          const float e0 = s0 > -INFINITY ? fast_exp2(s0 - mx) : 0.f, e1 = s1 > -INFINITY ? fast_exp2(s1 - mx) : 0.f;
           const float l = warp_sum(e0 + e1);
           asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
           if (tw == 0) {
@@ -303,11 +308,11 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
             float L = 0.f, acc = 0.f;
             for (int s = 0; s < n_act; ++s) {
               const float ms = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x), ls = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].y);
-              const float w = fast_exp2(ms - Mx);
+              const float w = ls > 0.f ? fast_exp2(ms - Mx) : 0.f;    // a fully masked split has m = -inf, l = 0
               L += ls * w;
               acc += __ldcg(p.part_o + ((size_t)bh * p.nsplit + s) * 128 + tt) * w;
             }
-            p.attn[(size_t)b * p.H + h * 128 + tt] = __float2bfloat16_rn(acc / L);
+            p.attn[(size_t)b * p.H + h * 128 + tt] = __float2bfloat16_rn(L > 0.f ? acc / L : 0.f);
             if (tt == 0) p.attn_counters[bh] = 0;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");   // scratch reuse by the next item

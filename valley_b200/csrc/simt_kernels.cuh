@@ -448,7 +448,14 @@ struct DecAttnParams {
   unsigned int* counters;           // [B*nH]
   __nv_bfloat16* out;               // [B, H]
   float scale_log2e;
+  const uint32_t* key_bits;         // [B, mask_words] bit k of row b = key k may be attended (attention_mask); never null
+  int mask_words;
 };
+
+// HF's 2-D attention_mask as one bit per cache position (vly_kv_set_key_mask); positions nobody masked are 1.
+__device__ __forceinline__ bool key_attendable(const uint32_t* __restrict__ bits, int k) {
+  return (__ldg(bits + (k >> 5)) >> (k & 31)) & 1u;
+}
 
 __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnParams p) {
   extern __shared__ __align__(16) float dsm[];
@@ -486,7 +493,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnPara
     d += __shfl_xor_sync(0xffffffffu, d, 4);
     d += __shfl_xor_sync(0xffffffffu, d, 2);
     d += __shfl_xor_sync(0xffffffffu, d, 1);
-    if (ok && hl == 0) sc[i] = d * p.scale_log2e;
+    if (ok && hl == 0) sc[i] = key_attendable(p.key_bits + (size_t)b * p.mask_words, k0 + i) ? d * p.scale_log2e : -INFINITY;
   }
   __syncthreads();
   float m = -INFINITY;
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnPara
   __syncthreads();
   float l = 0.f;
   for (int i = tid; i < nk; i += 128) {
-    const float e = fast_exp2(sc[i] - m);
+    const float e = sc[i] > -INFINITY ? fast_exp2(sc[i] - m) : 0.f;   // masked key (m itself may be -inf)
     sc[i] = e;
     l += e;
   }
@@ -546,7 +553,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnPara
         acc += __ldcg(p.part_o + ((size_t)bh * p.nsplit + s) * 128 + tid) * w;
       }
     }
-    p.out[(size_t)b * p.H + h * 128 + tid] = __float2bfloat16_rn(acc / L);
+    p.out[(size_t)b * p.H + h * 128 + tid] = __float2bfloat16_rn(L > 0.f ? acc / L : 0.f);
     if (tid == 0) p.counters[bh] = 0;
   }
 }

@@ -137,6 +137,16 @@ class ValleyKVCache:
     def reset(self):
         check(self._model._lib.vly_kv_reset(self._h, _stream()))
 
+    def set_attention_mask(self, attention_mask: Optional[torch.Tensor], total_len: int):
+        """HF's 2-D ``attention_mask`` [B, total_len] over cache positions 0..total_len-1 (past + new): a 0 means
+        the key is never attended (left padding from ``build_inputs``).  Later positions stay attendable."""
+        if attention_mask is None:
+            return
+        if attention_mask.dim() != 2 or tuple(attention_mask.shape) != (self.batch, total_len):
+            raise ValueError(f"attention_mask shape {tuple(attention_mask.shape)} != (batch {self.batch}, past+new {total_len})")
+        m = (attention_mask != 0).to(self._model.device, torch.uint8).contiguous()
+        check(self._model._lib.vly_kv_set_key_mask(self._h, m.data_ptr(), total_len, _stream()))
+
     def __del__(self):
         try:
             if getattr(self, "_h", None) is not None and self._model._ctx:
@@ -409,8 +419,9 @@ class ValleyLlamaForCausalLM:
     def forward(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
                 use_cache=None, output_attentions=None, output_hidden_states=None, images=None, return_dict=None):
         """ValleyLlamaForCausalLM.forward (valley_model.py:272-330).  logits are fp32 [B,S,V]
-        (the reference returns them in the model dtype; callers .float() them).  attention_mask is accepted and,
-        as on the reference's own inference paths (all-ones masks, model_worker.py:380-385), not applied."""
+        (the reference returns them in the model dtype; callers .float() them).  A 2-D attention_mask [B, past+S] masks
+        keys exactly as HF does (padding mask AND causal mask; position ids are not shifted -- the reference never
+        passes position_ids); rows that are themselves padding produce unspecified (finite) logits."""
         if inputs_embeds is None:
             if input_ids is None:
                 raise ValueError("You have to specify either input_ids or inputs_embeds")
@@ -425,6 +436,7 @@ class ValleyLlamaForCausalLM:
         cache = past_key_values if isinstance(past_key_values, ValleyKVCache) else None
         if cache is None:
             cache = self.new_cache(B)
+        cache.set_attention_mask(attention_mask, cache.get_seq_length() + S)
         if S == 1 and cache.get_seq_length() > 0 and input_ids is not None:
             logits, nxt = self._decode(cache, input_ids, True)
         else:
@@ -460,7 +472,8 @@ class ValleyLlamaForCausalLM:
                  temperature: float = 1.0, stopping_criteria=None, eos_token_id: Optional[int] = None, **kw):
         """Greedy (or temperature) generation == the loop of model_worker.py:371-397 / HF generate as called at
         valley_model.py:432.  Returns [B, S + n_new] like HF.  With no stopping criteria, greedy decoding runs
-        entirely on the device (CUDA-graph replay, no per-token host sync)."""
+        entirely on the device (CUDA-graph replay, no per-token host sync).  ``attention_mask`` [B, S] (left padding)
+        is honoured like HF generate does; generated positions are always attendable."""
         B, S = input_ids.shape
         room = self.config.max_position_embeddings - S
         n_new = max(0, min(max_new_tokens, room))
@@ -469,6 +482,7 @@ class ValleyLlamaForCausalLM:
         _, _, _, embeds, _ = self.prepare_inputs_labels_for_multimodal(input_ids, None, None, None, images)
         cache = self._borrow_cache(B)
         try:
+            cache.set_attention_mask(kw.get("attention_mask"), S)
             return self._generate_with_cache(cache, input_ids, embeds, n_new, do_sample, temperature, stopping_criteria, eos_token_id)
         finally:
             self._return_cache(cache)

@@ -44,7 +44,11 @@ VALLEY_13B = ShapeSpec("valley-13b", 5120, 40, 40, 13824, rms_norm_eps=1e-6)    
 TINY = ShapeSpec("tiny", 512, 2, 4, 1024, vocab_size=1032, vit_layers=3)               # parity-test size
 TINY_WIDE = ShapeSpec("tiny-wide", 768, 3, 6, 1536, vocab_size=2056, vit_layers=2, rms_norm_eps=1e-6)
 
-SPECS = {s.name: s for s in (VALLEY2_7B, VALLEY_13B, TINY, TINY_WIDE)}
+# one decoder layer / one ViT layer at the real widths: parity at the production shapes (K tails, 40 heads, V = 32008)
+SHAPE_7B_1L = ShapeSpec("shape-7b-1l", 4096, 1, 32, 11008, vit_layers=2)
+SHAPE_13B_1L = ShapeSpec("shape-13b-1l", 5120, 1, 40, 13824, rms_norm_eps=1e-6, vit_layers=2)
+
+SPECS = {s.name: s for s in (VALLEY2_7B, VALLEY_13B, TINY, TINY_WIDE, SHAPE_7B_1L, SHAPE_13B_1L)}
 
 
 def weight_shapes(spec: ShapeSpec, *, vision: bool = True, llm: bool = True) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
