@@ -147,6 +147,28 @@ int vly_llama_decode(vly_ctx* ctx, vly_kv* kv, const int64_t* tokens_dev, int64_
 int vly_generate_greedy(vly_ctx* ctx, vly_kv* kv, const int64_t* first_tokens_dev, int n_steps, int64_t* out_tokens_dev,
                         void* stream);
 
+/* ---- token selection on the device (model_worker.py:388-397; HF generate as called at valley_model.py:432) ----
+ * temperature < 1e-4: arg-max (model_worker.py:390-391); otherwise multinomial(softmax(logits / temperature)) (:392-395), drawn
+ * with the Gumbel-max identity from counter-based Philox noise keyed by `seed` -- fused into the arg-max epilogue of the decode
+ * step, so sampling costs no extra pass and no host round trip.  eos_token_id >= 0: a row that emits it is finished (:396-397);
+ * finished rows emit pad_token_id (HF generate) and once every row has finished the remaining steps are skipped. */
+typedef struct {
+  float temperature;
+  uint64_t seed;
+  int64_t eos_token_id;      /* -1: none */
+  int64_t pad_token_id;
+} vly_sampling;
+
+/* the first generated token: select from the prefill's last-position logits [B,V] fp32 (vly_llama_prefill logits_mode 1);
+ * starts a generation (clears the finished flags). */
+int vly_sample_logits(vly_ctx* ctx, vly_kv* kv, const float* logits_dev, const vly_sampling* sampling, int64_t* tokens_out_dev,
+                      void* stream);
+/* vly_generate_greedy with token selection per `sampling` (NULL = greedy, no stop token).  steps_done_dev (optional, device
+ * int32) receives the number of steps actually executed: n_steps, or fewer when every row reached eos -- columns
+ * [0, steps_done) of out_tokens_dev are valid. */
+int vly_generate(vly_ctx* ctx, vly_kv* kv, const int64_t* first_tokens_dev, int n_steps, int64_t* out_tokens_dev,
+                 const vly_sampling* sampling, int* steps_done_dev, void* stream);
+
 /* ---- introspection for bench / tests ---- */
 int vly_kernel_launch_count(vly_ctx* ctx, int64_t* out);   /* kernels launched by this ctx so far */
 int vly_num_sms(vly_ctx* ctx, int* out);

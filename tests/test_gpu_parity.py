@@ -299,6 +299,107 @@ def test_left_padded_golden_reference_logits():
         cur = lp["decode_logits"][:, i].argmax(-1)[:, None]
 
 
+def _sample_direct(m, cache, logits, temperature, seed, eos=-1, pad=0):
+    from valley_b200._lib import VlySampling, check
+    import ctypes as C
+    sp = VlySampling(float(temperature), int(seed), int(eos), int(pad))
+    out = torch.empty(cache.batch, dtype=torch.int64, device="cuda")
+    lg = logits.reshape(cache.batch, -1).float().contiguous()
+    check(m._lib.vly_sample_logits(m._ctx, cache._h, lg.data_ptr(), C.byref(sp), out.data_ptr(), None))
+    return out
+
+
+def test_device_sampler_draws_softmax_of_logits_over_temperature():
+    """model_worker.py:392-395: probs = softmax(logits / T); token = multinomial(probs).  The device draws it by Gumbel-max over
+    Philox noise: goodness of fit of 6000 draws (one seed each) against the oracle's softmax, determinism per seed, and the
+    temperature -> 0 limit (arg-max, :390-391)."""
+    from scipy import stats
+    spec, sd, m = get("tiny")
+    V, T, N = spec.vocab_size, 0.7, 6000
+    cache = m.new_cache(1, 128)
+    logits = (torch.randn(1, V, generator=torch.Generator().manual_seed(11)) * 1.5).cuda()
+    probs = torch.softmax(logits[0].double().cpu() / T, -1)
+    draws = torch.stack([_sample_direct(m, cache, logits, T, 1000 + i) for i in range(N)]).cpu().reshape(-1)
+    assert int(draws.min()) >= 0 and int(draws.max()) < V
+    counts = torch.bincount(draws, minlength=V).double()
+    big = probs * N >= 10                         # individual cells for likely tokens, one pooled cell for the tail
+    obs = torch.cat([counts[big], counts[~big].sum()[None]])
+    exp = torch.cat([probs[big] * N, (probs[~big].sum() * N)[None]])
+    chi2 = float(((obs - exp) ** 2 / exp).sum())
+    assert chi2 < stats.chi2.ppf(1 - 1e-6, df=len(obs) - 1), (chi2, len(obs))
+    assert len(obs) > 50 and counts.max() < 0.5 * N          # a real spread, not one token
+    a, b = _sample_direct(m, cache, logits, T, 77), _sample_direct(m, cache, logits, T, 77)
+    assert torch.equal(a, b)
+    assert int(_sample_direct(m, cache, logits, 1e-5, 5)) == int(logits.argmax())
+    # a sharper temperature concentrates mass on the arg-max
+    cold = torch.stack([_sample_direct(m, cache, logits, 0.05, 9000 + i) for i in range(200)]).cpu().reshape(-1)
+    p_cold = torch.softmax(logits[0].double().cpu() / 0.05, -1)
+    assert abs(float((cold == int(logits.argmax())).double().mean()) - float(p_cold.max())) < 0.15
+
+
+@pytest.mark.parametrize("B", [1, 2, 6])
+def test_fused_sampling_equals_standalone_selection_on_the_same_logits(B):
+    """generate(do_sample=True) selects inside the decode step (persistent kernel epilogue for B <= 4, post-step kernel for the
+    per-op path).  Teacher-forcing the drawn ids through forward() and selecting from each step's logits with the stand-alone
+    kernel under the same (seed, row, position) counter must give the same ids: the fused path is the same distribution."""
+    spec, sd, m = get("tiny")
+    n, T = 7, 0.8
+    ids, px = syn.make_prompt_ids(spec, B, 2, 5), syn.make_pixels(B, 2, 5)
+    torch.manual_seed(4242)
+    gen = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n, do_sample=True, temperature=T)[:, ids.shape[1]:]
+    assert gen.shape == (B, n)
+    torch.manual_seed(4242)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    out = m(input_ids=ids.cuda(), images=px.cuda())
+    cache, toks = out.past_key_values, []
+    toks.append(_sample_direct(m, cache, out.logits[:, -1], T, seed))
+    for i in range(1, n):
+        o = m(input_ids=toks[-1][:, None], past_key_values=cache)
+        toks.append(_sample_direct(m, cache, o.logits[:, -1], T, seed))
+    assert torch.equal(torch.stack(toks, 1), gen)
+    greedy = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n)[:, ids.shape[1]:]
+    assert not torch.equal(greedy, gen)                      # T = 0.8 on ~flat random-init logits: not the arg-max path
+    torch.manual_seed(4243)
+    other = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n, do_sample=True, temperature=T)[:, ids.shape[1]:]
+    assert not torch.equal(other, gen)                       # another seed, another draw
+
+
+@pytest.mark.parametrize("B", [1, 2, 5])
+def test_eos_stops_on_the_device_like_hf_generate(B):
+    """model_worker.py:396-397 / HF generate: a row that emits eos is finished, finished rows are padded, generation ends when
+    every row is finished.  Expected ids are derived from the free-running greedy ids (rows are independent)."""
+    spec, sd, m = get("tiny")
+    n, PAD = 9, 7
+    ids, px = syn.make_prompt_ids(spec, B, 2, 6), syn.make_pixels(B, 2, 6)
+    S = ids.shape[1]
+    g = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n)[:, S:].cpu()
+    i0 = next(i for i in range(2, n) if g[0, i] not in g[0, :i])
+    eos = int(g[0, i0])
+    exp, stop = g.clone(), []
+    for b in range(B):
+        hit = (g[b] == eos).nonzero()
+        k = int(hit[0]) if len(hit) else n - 1
+        exp[b, k + 1:] = PAD
+        stop.append(k if len(hit) else n - 1)
+    n_valid = max(stop) + 1
+    got = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n, eos_token_id=eos, pad_token_id=PAD)
+    assert got.shape[1] == S + n_valid, (got.shape, n_valid)
+    assert torch.equal(got[:, S:].cpu(), exp[:, :n_valid])
+    if B == 1:      # the host-visible loop (stopping criteria present) ends at the same place
+        never = lambda seq, scores: False
+        host = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n, eos_token_id=eos, stopping_criteria=[never])
+        assert torch.equal(host, got)
+    # the recycled cache is clean again: same greedy ids as before
+    g2 = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n)[:, S:].cpu()
+    assert torch.equal(g, g2)
+    # and a cache used directly reports the true length after an early stop
+    if B <= 4:      # (the per-op path of larger batches keeps stepping with pad tokens instead of skipping the steps)
+        cache = m.new_cache(B)
+        emb = m.prepare_inputs_labels_for_multimodal(ids, None, None, None, px)[3]
+        full = m._generate_with_cache(cache, ids, emb, n, False, 1.0, None, eos, PAD)
+        assert cache.get_seq_length() == S + (full.shape[1] - S) - 1
+
+
 def test_cache_capacity_is_enforced():
     spec, sd, m = get("tiny")
     ids = syn.make_prompt_ids(spec, 1, 2, 0)

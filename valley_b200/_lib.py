@@ -31,6 +31,10 @@ class VlyTokens(C.Structure):
                                           "vi_frame_token", "vi_start_token", "vi_end_token")]
 
 
+class VlySampling(C.Structure):
+    _fields_ = [("temperature", C.c_float), ("seed", C.c_uint64), ("eos_token_id", C.c_int64), ("pad_token_id", C.c_int64)]
+
+
 VLY_OK, VLY_ERR_INVALID, VLY_ERR_CUDA, VLY_ERR_STATE = 0, -1, -2, -3
 VLY_ERR_IM_COUNT, VLY_ERR_IM_CUT, VLY_ERR_INDEX = -10, -11, -12
 VLY_F32, VLY_BF16, VLY_F16 = 0, 1, 2
@@ -62,6 +66,8 @@ SIGNATURES = {
     "vly_llama_prefill": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "vly_llama_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "vly_generate_greedy": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "vly_sample_logits": (_i, [_vp, _vp, _vp, _p(VlySampling), _vp, _vp]),
+    "vly_generate": (_i, [_vp, _vp, _vp, _i, _vp, _p(VlySampling), _vp, _vp]),
     "vly_kernel_launch_count": (_i, [_vp, _p(_i64)]),
     "vly_num_sms": (_i, [_vp, _p(_i)]),
     "vly_test_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),

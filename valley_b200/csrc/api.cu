@@ -122,11 +122,14 @@ struct vly_ctx {
   Buf w_xlocal;
 };
 
+struct vly_kv;
+static int sync_len(vly_kv* kv);
 struct vly_kv {
   vly_ctx* ctx;
   int B, Smax;
   bf16* cache = nullptr;  // [L][2][B][nH][Smax][128]
   int host_len = 0;
+  bool len_dirty = false;   // a stop token may have ended vly_generate early: host_len is re-read from the device on next use
   int* d_len = nullptr;   // device scalar
   int* d_step = nullptr;
   // decode workspace
@@ -144,6 +147,8 @@ struct vly_kv {
   int n_phases = 0;
   unsigned int* grid_counter = nullptr;
   long long* dbg = nullptr;
+  SampleState* d_sample = nullptr;    // token selection state read by every decode step (sampling.cuh)
+  bool sample_dirty = false;          // device state is not the plain-greedy default
   uint32_t* key_bits = nullptr;       // [B, Smax/32] attention_mask bits (1 = attend); all ones unless vly_kv_set_key_mask
   bool masked = false;
   int mask_words() const { return Smax / 32; }
@@ -153,6 +158,15 @@ struct vly_kv {
   bf16* k_layer(int l) const { return cache + (size_t)l * layer_stride(); }
   bf16* v_layer(int l) const { return k_layer(l) + layer_stride() / 2; }
 };
+
+// after an eos-terminated vly_generate only the device knows how many steps ran (one blocking 4-byte read, off the hot path)
+static int sync_len(vly_kv* kv) {
+  if (!kv->len_dirty) return VLY_OK;
+  CK(cudaSetDevice(kv->ctx->cfg.device));
+  CK(cudaMemcpy(&kv->host_len, kv->d_len, 4, cudaMemcpyDeviceToHost));
+  kv->len_dirty = false;
+  return VLY_OK;
+}
 
 // decode implementation: 2 = one persistent cooperative kernel per step (default), 1 = per-op TMA-ring kernels + PDL,
 // 0 = per-op register-streaming kernels (generation 1).  VLY_DECODE=v1|ring|mega overrides (A/B measurements).
@@ -989,6 +1003,12 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   CK(cudaMalloc((void**)&kv->cur_tokens, (size_t)batch * 8));
   CK(cudaMalloc((void**)&kv->gen_tokens, (size_t)batch * kv->Smax * 8));
   CK(cudaMalloc((void**)&kv->dbg, 1024 * 8 * 8));
+  CK(cudaMalloc((void**)&kv->d_sample, sizeof(SampleState)));
+  {
+    SampleState s0 = {};
+    s0.inv_temp = 1.f; s0.eos = -1; s0.pad = 0;
+    CK(cudaMemcpy(kv->d_sample, &s0, sizeof(s0), cudaMemcpyHostToDevice));
+  }
   CK(cudaMalloc((void**)&kv->key_bits, (size_t)batch * kv->mask_words() * 4));
   CK(cudaMemset(kv->key_bits, 0xff, (size_t)batch * kv->mask_words() * 4));
   {  // phase table of the persistent decode-step kernel: execution order of one step
@@ -1017,7 +1037,7 @@ extern "C" void vly_kv_destroy(vly_kv* kv) {
   if (!kv) return;
   cudaSetDevice(kv->ctx->cfg.device);
   if (kv->graph) cudaGraphExecDestroy(kv->graph);
-  void* ps[] = {kv->key_bits, kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
+  void* ps[] = {kv->d_sample, kv->key_bits, kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
   for (void* p : ps)
     if (p) cudaFree(p);
   delete kv;
@@ -1025,6 +1045,7 @@ extern "C" void vly_kv_destroy(vly_kv* kv) {
 
 extern "C" int vly_kv_seq_len(vly_kv* kv, int* out) {
   if (!kv || !out) return fail(VLY_ERR_INVALID, "null");
+  TRY(sync_len(kv));
   *out = kv->host_len;
   return VLY_OK;
 }
@@ -1033,6 +1054,7 @@ extern "C" int vly_kv_reset(vly_kv* kv, void* stream) {
   if (!kv) return fail(VLY_ERR_INVALID, "null");
   CK(cudaSetDevice(kv->ctx->cfg.device));
   kv->host_len = 0;
+  kv->len_dirty = false;
   CK(cudaMemsetAsync(kv->d_len, 0, 8, (cudaStream_t)stream));
   if (kv->masked) {
     CK(cudaMemsetAsync(kv->key_bits, 0xff, (size_t)kv->B * kv->mask_words() * 4, (cudaStream_t)stream));
@@ -1071,6 +1093,7 @@ extern "C" int vly_kv_set_key_mask(vly_kv* kv, const uint8_t* mask_dev, int len,
 
 extern "C" int vly_kv_export(vly_ctx* c, vly_kv* kv, int layer, int which, void* out, void* stream) {
   if (!c || !kv || !out || layer < 0 || layer >= c->cfg.num_hidden_layers || (which != 0 && which != 1)) return fail(VLY_ERR_INVALID, "vly_kv_export: bad argument");
+  TRY(sync_len(kv));
   if (kv->host_len == 0) return VLY_OK;
   CK(cudaSetDevice(c->cfg.device));
   dim3 grid(kv->host_len, kv->B * c->cfg.num_attention_heads);
@@ -1287,6 +1310,7 @@ extern "C" int vly_llama_prefill(vly_ctx* c, vly_kv* kv, const void* inputs_embe
   if (logits_mode < 0 || logits_mode > 2 || (logits_mode && !logits_dev)) return fail(VLY_ERR_INVALID, "vly_llama_prefill: bad logits mode");
   std::lock_guard<std::mutex> lk(c->mu);
   if (!c->finalized || !c->has_llm) return fail(VLY_ERR_STATE, "vly_llama_prefill: LLM weights not finalised");
+  TRY(sync_len(kv));
   const int past = kv->host_len;
   if (past + S > kv->Smax) return fail(VLY_ERR_INVALID, "vly_llama_prefill: %d cached + %d new tokens exceed the cache capacity %d", past, S, kv->Smax);
   CK(cudaSetDevice(c->cfg.device));
@@ -1387,6 +1411,7 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   p.logits = kv->logits; p.part_val = kv->part_val; p.part_idx = kv->part_idx;
   p.next_tokens = kv->cur_tokens; p.out_tokens = kv->gen_tokens; p.out_stride = kv->Smax;
   p.grid_counter = kv->grid_counter;
+  p.sample = kv->d_sample;
   {
     static const bool want = getenv("VLY_MEGA_DBG") != nullptr;
     p.dbg = want ? kv->dbg : nullptr;
@@ -1435,6 +1460,42 @@ static int enqueue_full_step(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
     const int nb = (kv->B - b0) < 4 ? (kv->B - b0) : 4;
     TRY(enqueue_decode_step(c, kv, b0, nb, b0 + 4 >= kv->B, st));
   }
+  // per-op paths: temperature sampling / eos bookkeeping as one more launch over the step's logits (returns at once when greedy)
+  if (kv->B <= kMaxSampleRows) {
+    sample_rows_kernel<<<1, 1024, 0, st>>>(kv->logits, kv->B, c->cfg.vocab_size, kv->d_sample, kv->d_len, kv->d_step, kv->cur_tokens,
+                                           kv->gen_tokens, kv->Smax, 0);
+    c->launches++;
+    CKL();
+  }
+  return VLY_OK;
+}
+
+// ---- token selection state ----
+__global__ void set_sample_state_kernel(SampleState* s, float inv_temp, int enabled, uint32_t k0, uint32_t k1, long long eos, long long pad,
+                                        int reset_done) {
+  if (threadIdx.x == 0) {
+    s->inv_temp = inv_temp; s->enabled = enabled; s->seed_lo = k0; s->seed_hi = k1; s->eos = eos; s->pad = pad;
+    if (reset_done) { s->all_done = 0; s->steps_valid = 0; }
+  }
+  if (reset_done && threadIdx.x < kMaxSampleRows) s->done[threadIdx.x] = 0;
+}
+
+// sampling == nullptr: plain greedy, no stop token (skipped when the device state already says so)
+static int set_sampling(vly_ctx* c, vly_kv* kv, const vly_sampling* sp, bool reset_done, cudaStream_t st) {
+  if (!sp) {
+    if (!kv->sample_dirty) return VLY_OK;
+    set_sample_state_kernel<<<1, 64, 0, st>>>(kv->d_sample, 1.f, 0, 0, 0, -1, 0, 1);
+    kv->sample_dirty = false;
+  } else {
+    if (kv->B > kMaxSampleRows) return fail(VLY_ERR_INVALID, "sampling / eos bookkeeping supports at most %d sequences per cache", kMaxSampleRows);
+    const bool on = sp->temperature >= 1e-4f;         // model_worker.py:390: below that the reference takes the arg-max
+    set_sample_state_kernel<<<1, 64, 0, st>>>(kv->d_sample, on ? 1.f / sp->temperature : 1.f, on ? 1 : 0, (uint32_t)sp->seed,
+                                              (uint32_t)(sp->seed >> 32), sp->eos_token_id < 0 ? -1 : sp->eos_token_id, sp->pad_token_id,
+                                              reset_done ? 1 : 0);
+    kv->sample_dirty = true;
+  }
+  c->launches++;
+  CKL();
   return VLY_OK;
 }
 
@@ -1458,16 +1519,45 @@ static int build_graph(vly_ctx* c, vly_kv* kv) {
   return VLY_OK;
 }
 
-extern "C" int vly_generate_greedy(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, int n_steps, int64_t* out_tokens, void* stream) {
-  if (!c || !kv || !first_tokens || n_steps <= 0 || kv->ctx != c) return fail(VLY_ERR_INVALID, "vly_generate_greedy: bad argument");
+extern "C" int vly_sample_logits(vly_ctx* c, vly_kv* kv, const float* logits, const vly_sampling* sp, int64_t* tokens_out, void* stream) {
+  if (!c || !kv || !logits || !sp || !tokens_out || kv->ctx != c) return fail(VLY_ERR_INVALID, "vly_sample_logits: bad argument");
   std::lock_guard<std::mutex> lk(c->mu);
-  if (kv->host_len + n_steps > kv->Smax) return fail(VLY_ERR_INVALID, "vly_generate_greedy: %d cached + %d steps exceed the cache capacity %d", kv->host_len, n_steps, kv->Smax);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(set_sampling(c, kv, sp, true, st));
+  sample_rows_kernel<<<1, 1024, 0, st>>>(logits, kv->B, c->cfg.vocab_size, kv->d_sample, kv->d_len, kv->d_step, (long long*)tokens_out, nullptr, 0, 1);
+  c->launches++;
+  CKL();
+  return VLY_OK;
+}
+
+static int generate_impl(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, int n_steps, int64_t* out_tokens, const vly_sampling* sp,
+                         int* steps_done_dev, void* stream);
+
+extern "C" int vly_generate_greedy(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, int n_steps, int64_t* out_tokens, void* stream) {
+  return generate_impl(c, kv, first_tokens, n_steps, out_tokens, nullptr, nullptr, stream);
+}
+
+extern "C" int vly_generate(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, int n_steps, int64_t* out_tokens, const vly_sampling* sp,
+                            int* steps_done_dev, void* stream) {
+  return generate_impl(c, kv, first_tokens, n_steps, out_tokens, sp, steps_done_dev, stream);
+}
+
+static int generate_impl(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, int n_steps, int64_t* out_tokens, const vly_sampling* sp,
+                         int* steps_done_dev, void* stream) {
+  if (!c || !kv || !first_tokens || n_steps <= 0 || kv->ctx != c) return fail(VLY_ERR_INVALID, "vly_generate: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  TRY(sync_len(kv));
+  if (kv->host_len + n_steps > kv->Smax) return fail(VLY_ERR_INVALID, "vly_generate: %d cached + %d steps exceed the cache capacity %d", kv->host_len, n_steps, kv->Smax);
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   static const bool no_graph = getenv("VLY_NO_GRAPH") != nullptr;   // profiling aid: eager launches instead of graph replay
   if (!no_graph) TRY(build_graph(c, kv));
+  // with a sampling struct the eos flags raised by vly_sample_logits (the first token) are kept; greedy starts clean
+  TRY(set_sampling(c, kv, sp, false, st));
   CK(cudaMemcpyAsync(kv->cur_tokens, first_tokens, (size_t)kv->B * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(kv->d_step, 0, 4, st));
+  if (steps_done_dev) CK(cudaMemsetAsync(&kv->d_sample->steps_valid, 0, 4, st));
   for (int i = 0; i < n_steps; ++i) {
     if (no_graph) TRY(enqueue_full_step(c, kv, st));
     else CK(cudaGraphLaunch(kv->graph, st));
@@ -1476,17 +1566,22 @@ extern "C" int vly_generate_greedy(vly_ctx* c, vly_kv* kv, const int64_t* first_
   if (out_tokens)
     CK(cudaMemcpy2DAsync(out_tokens, (size_t)n_steps * 8, kv->gen_tokens, (size_t)kv->Smax * 8, (size_t)n_steps * 8, kv->B,
                          cudaMemcpyDeviceToDevice, st));
+  if (steps_done_dev)      // (zeroed below, before the first step)
+    CK(cudaMemcpyAsync(steps_done_dev, &kv->d_sample->steps_valid, 4, cudaMemcpyDeviceToDevice, st));
   kv->host_len += n_steps;
+  if (sp && sp->eos_token_id >= 0) kv->len_dirty = true;      // the loop may have stopped early: the device holds the true length
   return VLY_OK;
 }
 
 extern "C" int vly_llama_decode(vly_ctx* c, vly_kv* kv, const int64_t* tokens, int64_t* next_tokens, void* logits_dev, void* stream) {
   if (!c || !kv || !tokens || kv->ctx != c) return fail(VLY_ERR_INVALID, "vly_llama_decode: bad argument");
   std::lock_guard<std::mutex> lk(c->mu);
+  TRY(sync_len(kv));
   if (kv->host_len + 1 > kv->Smax) return fail(VLY_ERR_INVALID, "vly_llama_decode: cache full (%d)", kv->Smax);
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   TRY(build_graph(c, kv));
+  TRY(set_sampling(c, kv, nullptr, true, st));
   CK(cudaMemcpyAsync(kv->cur_tokens, tokens, (size_t)kv->B * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(kv->d_step, 0, 4, st));
   CK(cudaGraphLaunch(kv->graph, st));

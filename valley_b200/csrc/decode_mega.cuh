@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "decode_kernels.cuh"
+#include "sampling.cuh"
 
 namespace vly {
 
@@ -59,6 +60,7 @@ struct StepParams {
   long long* next_tokens;       // [B]
   long long* out_tokens;        // [B, out_stride]
   int out_stride;
+  SampleState* sample;          // token selection state (greedy / temperature sampling, eos bookkeeping); sampling.cuh
   unsigned int* grid_counter;   // zeroed by the host before every launch
   int n_stages;
   long long* dbg;               // optional [gridDim][8] cycle counters: sync, stage-x, weight loop, attention, full-wait
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
   int* team_flag = reinterpret_cast<int*>(wred + 16 * BMAX);                             // [4]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.sample->all_done) return;       // every sequence has produced its stop token: the remaining replays are no-ops
   if (tid == 0) {
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -191,6 +194,9 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
   const int ct = tid - 32;            // compute thread 0..511 (finalize warp: 512..543)
   const int cw = warp - 1;            // compute warp 0..15
   const int pos = *p.seq_len;
+  const bool samp_on = p.sample->enabled != 0;
+  const float samp_it = p.sample->inv_temp;
+  const uint32_t samp_k0 = p.sample->seed_lo, samp_k1 = p.sample->seed_hi;
   unsigned int sync_no = 0;
   long long t_sync = 0, t_stage = 0, t_loop = 0, t_attn = 0, t0 = clock64();
   // ---- phase -1: x = embed[token] (decode input) ----
@@ -476,7 +482,8 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
             } else if (d.type == PH_LOGITS) {
               const float y = t * rstd_s[b];
               if (ok && p.logits != nullptr) p.logits[(size_t)b * d.N + n] = y;
-              float bv = ok ? y : -INFINITY;
+              // greedy: the logit itself; sampling: logit / T + Gumbel noise (arg-max == multinomial(softmax(logits / T)))
+              float bv = ok ? (samp_on ? sample_score(y, samp_it, samp_k0, samp_k1, n, b, pos) : y) : -INFINITY;
               int bi = n;
 #pragma unroll
               for (int o = BMAX; o < NV; o <<= 1) {
@@ -546,14 +553,21 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
       if (lane == 0) {
-        p.next_tokens[b] = bi;
-        if (p.out_tokens != nullptr) p.out_tokens[(size_t)b * p.out_stride + *p.step] = bi;
+        const long long tok = sample_finish_row(p.sample, b, bi);
+        p.next_tokens[b] = tok;
+        if (p.out_tokens != nullptr) p.out_tokens[(size_t)b * p.out_stride + *p.step] = tok;
       }
     }
     asm volatile("bar.sync 7, 512;" ::: "memory");
     if (ct == 0) {
       *p.step += 1;
       *p.seq_len += 1;
+      p.sample->steps_valid += 1;
+      if (p.sample->eos >= 0) {
+        int all = 1;
+        for (int b = 0; b < p.B; ++b) all &= p.sample->done[b];
+        p.sample->all_done = all;
+      }
     }
   }
 }

@@ -20,7 +20,7 @@ from typing import Iterable, List, Optional, Tuple, Union
 import torch
 
 from . import _lib
-from ._lib import VlyConfig, VlyTokens, check
+from ._lib import VlySampling, VlyConfig, VlyTokens, check
 
 # valley/util/config.py:1-13
 IGNORE_INDEX = -100
@@ -483,14 +483,17 @@ class ValleyLlamaForCausalLM:
         cache = self._borrow_cache(B)
         try:
             cache.set_attention_mask(kw.get("attention_mask"), S)
-            return self._generate_with_cache(cache, input_ids, embeds, n_new, do_sample, temperature, stopping_criteria, eos_token_id)
+            return self._generate_with_cache(cache, input_ids, embeds, n_new, do_sample, temperature, stopping_criteria, eos_token_id,
+                                             kw.get("pad_token_id"))
         finally:
             self._return_cache(cache)
 
-    def _generate_with_cache(self, cache, input_ids, embeds, n_new, do_sample, temperature, stopping_criteria, eos_token_id):
+    def _generate_with_cache(self, cache, input_ids, embeds, n_new, do_sample, temperature, stopping_criteria, eos_token_id,
+                             pad_token_id=None):
         B = input_ids.shape[0]
         greedy = (not do_sample) or temperature < 1e-4
-        logits, nxt = self._prefill(cache, embeds, 0 if greedy else 1)
+        device_select = not stopping_criteria and not (greedy and eos_token_id is None) and B <= 64
+        logits, nxt = self._prefill(cache, embeds, 0 if (greedy and not device_select) else 1)
         ids_dev = input_ids.to(self.device, torch.int64)
         if greedy and not stopping_criteria and eos_token_id is None:
             out = torch.empty(B, n_new, dtype=torch.int64, device=self.device)
@@ -500,6 +503,26 @@ class ValleyLlamaForCausalLM:
                 check(self._lib.vly_generate_greedy(self._ctx, cache._h, nxt.data_ptr(), n_new - 1, rest.data_ptr(), _stream()))
                 out[:, 1:] = rest
             return torch.cat([ids_dev, out], dim=1)
+        if device_select:
+            # temperature sampling and/or a stop token, still without a per-token host sync: the selection (Gumbel-max over
+            # Philox noise) and the eos bookkeeping run inside the decode step; one 4-byte read at the end gives the length
+            eos = -1 if eos_token_id is None else int(eos_token_id)
+            pad = int(pad_token_id) if pad_token_id is not None else max(eos, 0)      # HF: pad defaults to eos
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())                         # torch.manual_seed() governs it
+            sp = VlySampling(0.0 if greedy else float(temperature), seed, eos, pad)
+            out = torch.empty(B, n_new, dtype=torch.int64, device=self.device)
+            first = torch.empty(B, dtype=torch.int64, device=self.device)
+            check(self._lib.vly_sample_logits(self._ctx, cache._h, logits.data_ptr(), C.byref(sp), first.data_ptr(), _stream()))
+            out[:, 0] = first
+            n_valid = 1
+            if n_new > 1:
+                rest = torch.empty(B, n_new - 1, dtype=torch.int64, device=self.device)
+                done = torch.zeros(1, dtype=torch.int32, device=self.device)
+                check(self._lib.vly_generate(self._ctx, cache._h, first.data_ptr(), n_new - 1, rest.data_ptr(), C.byref(sp),
+                                             done.data_ptr(), _stream()))
+                out[:, 1:] = rest
+                n_valid += int(done.item())
+            return torch.cat([ids_dev, out[:, :n_valid]], dim=1)
         # host-visible loop (stopping criteria / sampling / eos): one device->host sync per token, as in the reference
         seq = ids_dev
         for i in range(n_new):
