@@ -321,6 +321,39 @@ def main():
         return timed(f, 3, 2)[0]
     ms_prefill = prefill_only()
 
+    def decode_sampled():
+        """same steady-state decode with temperature sampling + eos bookkeeping selected inside the step (f-1)"""
+        import ctypes as C
+        from valley_b200._lib import VlySampling, check
+        cache = model.new_cache(vhi - vlo)
+        _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, None)
+        _, nxt = model._prefill(cache, emb, 0)
+        sp = VlySampling(0.8, 1234, spec.vocab_size + 5, 0)          # an eos id that can never be drawn: bookkeeping on, no early stop
+        out = torch.empty(vhi - vlo, N_NEW, dtype=torch.int64, device="cuda")
+        def run(n):
+            check(model._lib.vly_generate(model._ctx, cache._h, nxt.data_ptr(), n, out.data_ptr(), C.byref(sp), None,
+                                          torch.cuda.current_stream().cuda_stream))
+        run(8)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(N_NEW - 8)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / (N_NEW - 8)
+    ms_dec_sampled = decode_sampled()
+
+    def preprocess_only():
+        """f-2: 8 decoded 720p uint8 frames -> [8,3,224,224] fp16 (device-resident input; and from pinned host memory)"""
+        from valley_b200 import video
+        g = torch.Generator().manual_seed(5)
+        host = torch.randint(0, 256, (N_FRAMES, 720, 1280, 3), dtype=torch.uint8, generator=g).pin_memory()
+        dev = host.cuda()
+        ms_dev = timed(lambda: video.preprocess_frames(model, dev), 20, 3)[0]
+        ms_host = timed(lambda: video.preprocess_frames(model, host), 20, 3)[0]
+        return ms_dev, ms_host, host
+    ms_pre_dev, ms_pre_host, pre_host = preprocess_only()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -353,6 +386,11 @@ def main():
             "achieved": fps8 * gf / 1e3, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": fps8 * gf / 1e3 / pk["tf_burst"],
             "gflop_per_frame": gf, "peak_source": pk["src"],
             "sweep_frac": {k: v * gf / 1e3 / pk["tf_sust"] for k, v in sweep.items()}},
+        "decode_sampled_ms_per_token": ms_dec_sampled,
+        "preprocess": {"workload": "8 frames 720x1280x3 uint8 -> Resize(256, PIL bilinear) -> CenterCrop(224) -> CLIP normalise -> [8,3,224,224] fp16",
+                       "frames_per_s": world * N_FRAMES / (ms_pre_dev / 1e3), "ms_8_frames": ms_pre_dev,
+                       "e2e_frames_per_s": world * N_FRAMES / (ms_pre_host / 1e3), "e2e_ms_8_frames": ms_pre_host,
+                       "h2d_bytes": int(pre_host.numel())},
         "weights_load_s": t_load,
         "tokens_match_e2e": bool(torch.equal(toks.cpu(), toks_e2e)),
     }
@@ -360,6 +398,11 @@ def main():
         r = cpu_reference_arm(spec)
         line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                                 "vit_frames_per_s": r["vit_frames_per_s"], "decode_tokens_per_s": r["decode_tokens_per_s"]}
+        from oracle import preprocess_oracle as PO          # the reference's PIL pipeline, executed by Pillow (1 core, as load_video runs it)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            PO.pil_pipeline(pre_host.numpy())
+        line["cpu_baseline"]["preprocess_frames_per_s"] = 3 * N_FRAMES / (time.perf_counter() - t0)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -95,6 +95,18 @@ int vly_vit_encode_gather(vly_ctx* ctx, const void* pixels_dev, int pixel_dtype,
 /* enqueue after the kernels that read the gather buffer: lets the peers overwrite it in their next vly_vit_encode_gather */
 int vly_gather_release(vly_ctx* ctx, void* stream);
 
+/* ---- frame preprocessing: what load_video does to the decoded uint8 frames before the vision tower
+ * (valley/util/data_util.py:271-281): Resize(256) [PIL.Image.BILINEAR: video_transform.py:63-66 swaps the names] ->
+ * CenterCrop(224) -> /255 -> CLIP mean/std.  Bit-exact with the reference (Pillow's 8-bit two-pass fixed-point convolution).
+ *   vly_preprocess_plan   : host, exact: resized size (video_transform.py:56-60, :74-81) and crop origin (:542-543).  No GPU.
+ *   vly_resample_coeffs   : host, exact: Pillow's precompute_coeffs + normalize_coeffs_8bpc for the triangle filter.
+ *                           kk == NULL queries ksize only; else xmin[out], count[out], kk[out * ksize].  No GPU.
+ *   vly_preprocess_frames : frames_dev [T,H,W,3] uint8 (decord's get_batch layout, data_util.py:262) -> out_dev [T,3,224,224]
+ *                           of out_dtype (frames first, as every caller permutes it: model_worker.py:337, valley_model.py:430). */
+int vly_preprocess_plan(int H, int W, int* new_h, int* new_w, int* crop_y, int* crop_x);
+int vly_resample_coeffs(int in_size, int out_size, int* ksize_out, int32_t* xmin, int32_t* count, int32_t* kk);
+int vly_preprocess_frames(vly_ctx* ctx, const uint8_t* frames_dev, int T, int H, int W, int out_dtype, void* out_dev, void* stream);
+
 /* ---- mm_projector over every token, == encode_images' projection (valley_model.py:187-190):
  * feats [rows,1024] bf16 -> out [rows,hidden] bf16 */
 int vly_project(vly_ctx* ctx, const void* feats_dev, int64_t rows, void* out_dev, void* stream);

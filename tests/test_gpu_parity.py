@@ -400,6 +400,54 @@ def test_eos_stops_on_the_device_like_hf_generate(B):
         assert cache.get_seq_length() == S + (full.shape[1] - S) - 1
 
 
+@pytest.mark.parametrize("h,w", [(360, 640), (640, 360), (256, 340), (300, 256), (200, 150), (224, 224), (720, 1280), (255, 257), (481, 853)])
+def test_frame_preprocessing_is_bit_exact(h, w):
+    """vly_preprocess_frames vs the oracle (same clip) and vs the REFERENCE's own output (tests/golden/ref_preprocess.pt, written
+    by running valley/data/video_transform.py): integer stage and fp32 output bit for bit; fp16 / bf16 = RN of the fp32 result."""
+    import hashlib
+    import numpy as np
+    from oracle import preprocess_oracle as P
+    from valley_b200 import video
+    from test_oracle_golden import _clip
+    spec, sd, m = get("tiny")
+    g = torch.load(os.path.join(GOLD, "ref_preprocess.pt"))[(h, w)]
+    clip = _clip(h, w, g["seed"])
+    ref = P.preprocess_frames(clip)
+    out = video.preprocess_frames(m, torch.from_numpy(clip), torch.float32).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == g["sha_f32"]
+    for dt in (torch.float16, torch.bfloat16):
+        lo = video.preprocess_frames(m, torch.from_numpy(clip).cuda(), dt).cpu()
+        assert torch.equal(lo, torch.from_numpy(ref).to(dt))
+    # T = 5 frames, device-resident input, through the reader-style entry point
+    class Reader:
+        def __init__(self, frames): self.f = frames
+        def __len__(self): return len(self.f)
+        def get_batch(self, idx): return torch.from_numpy(self.f[np.asarray(idx)])
+        def get_avg_fps(self): return 2.2
+    many = np.concatenate([clip] * 6)[:11]
+    got = video.load_video(m, Reader(many), "fixed", 5, dtype=torch.float32).cpu().numpy()
+    assert np.array_equal(got, P.preprocess_frames(many[P.fixed_frame_indices(11, 5)]))
+    got = video.load_video(m, Reader(many), "fps", fps_number=0.5, dtype=torch.float32).cpu().numpy()
+    assert np.array_equal(got, P.preprocess_frames(many[P.fps_frame_indices(11, 2.2, 0.5)]))
+
+
+def test_preprocessed_frames_feed_the_vision_tower():
+    """uint8 frames -> preprocess -> encode_images == oracle preprocessing -> oracle ViT (same tolerance as the ViT test)."""
+    import numpy as np
+    from oracle import preprocess_oracle as P
+    from valley_b200 import video
+    from test_oracle_golden import _clip
+    spec, sd, m = get("tiny")
+    clip = np.concatenate([_clip(360, 640, 3), _clip(360, 640, 4)])[:3]
+    px = video.preprocess_frames(m, torch.from_numpy(clip), torch.float16)
+    got = m.get_model().vision_tower(px).selected_hidden_state
+    with torch.no_grad():
+        want = O.vit_hidden_state(sd, torch.from_numpy(P.preprocess_frames(clip)).half().float(), spec.mm_vision_select_layer,
+                                  num_layers=spec.vit_layers, heads=spec.vit_heads)
+    check_close(got, want, what="ViT on device-preprocessed frames")
+
+
 def test_cache_capacity_is_enforced():
     spec, sd, m = get("tiny")
     ids = syn.make_prompt_ids(spec, 1, 2, 0)

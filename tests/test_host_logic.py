@@ -126,3 +126,32 @@ def test_empty_and_degenerate_inputs():
     assert code == 0
     code, smap, iidx = plan(torch.full((2, 4), 5, dtype=torch.int64), 0, vly_tokens(spec))
     assert code == 0 and (smap == -1).all() and iidx.tolist() == [-1, -1]
+
+
+@pytest.mark.parametrize("h,w", [(360, 640), (640, 360), (256, 340), (300, 256), (200, 150), (224, 224), (720, 1280), (255, 257),
+                                 (481, 853), (1080, 1920), (257, 255), (2160, 3840), (258, 258)])
+def test_preprocess_plan_and_tables_match_oracle(h, w):
+    """Host side of vly_preprocess_frames (no GPU): resized size, crop origin and Pillow's fixed-point tables, exact."""
+    import numpy as np
+    from oracle import preprocess_oracle as P
+    from valley_b200 import video
+    nh, nw, cy, cx = video.preprocess_plan(h, w)
+    assert (nh, nw) == P.resize_sizes(h, w)
+    assert (cy, cx) == P.crop_origin(nh, nw)
+    for n_in, n_out in ((h, nh), (w, nw)):
+        k, xmin, cnt, kk = video.resample_coeffs(n_in, n_out)
+        ok, oxmin, ocnt, okk = P.bilinear_coeffs(n_in, n_out)
+        assert k == ok and np.array_equal(xmin, oxmin) and np.array_equal(cnt, ocnt) and np.array_equal(kk, okk)
+
+
+def test_frame_index_selection_matches_oracle():
+    import numpy as np
+    from oracle import preprocess_oracle as P
+    from valley_b200 import video
+    for n in (1, 7, 8, 9, 100, 1234):
+        assert np.array_equal(video.fixed_frame_indices(n), P.fixed_frame_indices(n))
+        assert np.array_equal(video.fixed_frame_indices(n), np.linspace(0, n - 1, 8).astype(np.int_))
+    for n, fps in ((300, 29.97), (50, 24.0), (1000, 59.94)):
+        assert np.array_equal(video.fps_frame_indices(n, fps), P.fps_frame_indices(n, fps))
+    with pytest.raises(ValueError):
+        video.preprocess_plan(0, 10)

@@ -71,3 +71,30 @@ def test_oracle_left_padded_batch_matches_reference(name):
             lg = O.causal_lm_forward(sd, cfg, tok, cur, None, cache, attention_mask=mask)[:, -1]
             assert torch.allclose(lg, lp["decode_logits"][:, i], rtol=1e-4, atol=1e-5)
             cur = lg.argmax(-1)[:, None]
+
+
+def _clip(h, w, seed):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    a = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    b = np.stack([(xx * 255 // max(w - 1, 1)), (yy * 255 // max(h - 1, 1)), ((xx + yy) % 256)], -1)
+    b = np.clip(b + rs.randint(-3, 4, b.shape), 0, 255).astype(np.uint8)
+    return np.stack([a, b])
+
+
+def test_preprocess_oracle_matches_reference_fixture():
+    """load_video's PIL pipeline (Resize(256) BILINEAR -> CenterCrop(224) -> /255 -> mean/std), bit for bit."""
+    import hashlib
+    import numpy as np
+    from oracle import preprocess_oracle as P
+    gold = torch.load(os.path.join(GOLD, "ref_preprocess.pt"))
+    assert len(gold) >= 9
+    for (h, w), g in gold.items():
+        clip = _clip(h, w, g["seed"])
+        u8 = P.preprocess_frames(clip, return_uint8=True)
+        f = P.preprocess_frames(clip)
+        assert hashlib.sha256(np.ascontiguousarray(u8).tobytes()).hexdigest() == g["sha_u8"], (h, w)
+        assert hashlib.sha256(np.ascontiguousarray(f).tobytes()).hexdigest() == g["sha_f32"], (h, w)
+        assert np.array_equal(f[:, :, ::9, ::7], g["sub_f32"].numpy())
+        assert np.array_equal(P.pil_pipeline(clip), f)                # the Pillow-executed pipeline bench.py times as the CPU baseline

@@ -53,6 +53,9 @@ SIGNATURES = {
     "vly_gather_open_peers": (_i, [_vp, _vp, _i, _i]),
     "vly_vit_encode_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "vly_gather_release": (_i, [_vp, _vp]),
+    "vly_preprocess_plan": (_i, [_i, _i, _p(_i), _p(_i), _p(_i), _p(_i)]),
+    "vly_resample_coeffs": (_i, [_i, _i, _p(_i), _p(C.c_int32), _p(C.c_int32), _p(C.c_int32)]),
+    "vly_preprocess_frames": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "vly_project": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "vly_pool_project": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "vly_build_splice_map": (_i, [_p(_i64), _i, _i, _i, _p(VlyTokens), _p(C.c_int32), _p(C.c_int32)]),

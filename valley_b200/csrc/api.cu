@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -20,6 +21,7 @@
 #include "simt_kernels.cuh"
 #include "decode_kernels.cuh"
 #include "decode_mega.cuh"
+#include "preprocess.cuh"
 
 using namespace vly;
 typedef __nv_bfloat16 bf16;
@@ -120,6 +122,10 @@ struct vly_ctx {
   int* g_peer_flags[8] = {};
   int g_world = 0, g_rank = 0, g_epoch = 0;
   Buf w_xlocal;
+  // frame preprocessing: strip + coefficient tables of the last geometry seen
+  Buf w_strip, w_tables;
+  int pre_H = 0, pre_W = 0;
+  PreprocParams pre = {};
 };
 
 struct vly_kv;
@@ -1589,6 +1595,54 @@ extern "C" int vly_llama_decode(vly_ctx* c, vly_kv* kv, const int64_t* tokens, i
   if (next_tokens) CK(cudaMemcpyAsync(next_tokens, kv->cur_tokens, (size_t)kv->B * 8, cudaMemcpyDeviceToDevice, st));
   if (logits_dev) CK(cudaMemcpyAsync(logits_dev, kv->logits, (size_t)kv->B * c->cfg.vocab_size * 4, cudaMemcpyDeviceToDevice, st));
   kv->host_len += 1;
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame preprocessing (load_video's Resize(256) -> CenterCrop(224) -> /255 -> CLIP mean/std), SURVEY 8 f-2
+// ------------------------------------------------------------------------------------------------
+extern "C" int vly_preprocess_frames(vly_ctx* c, const uint8_t* frames, int T, int H, int W, int out_dtype, void* out, void* stream) {
+  if (!c || !frames || !out || T <= 0 || H <= 0 || W <= 0 || out_dtype < VLY_F32 || out_dtype > VLY_F16)
+    return fail(VLY_ERR_INVALID, "vly_preprocess_frames: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  PreprocParams& p = c->pre;
+  if (c->pre_H != H || c->pre_W != W) {      // new geometry: rebuild the fixed-point tables on the host (exact, Pillow's arithmetic)
+    int nh, nw, cy, cx, kh = 0, kv = 0;
+    TRY(vly_preprocess_plan(H, W, &nh, &nw, &cy, &cx));
+    TRY(vly_resample_coeffs(W, nw, &kh, nullptr, nullptr, nullptr));
+    TRY(vly_resample_coeffs(H, nh, &kv, nullptr, nullptr, nullptr));
+    std::vector<int32_t> tab((size_t)nw * (2 + kh) + (size_t)nh * (2 + kv));
+    int32_t* xmin = tab.data(); int32_t* xcnt = xmin + nw; int32_t* xk = xcnt + nw;
+    int32_t* ymin = xk + (size_t)nw * kh; int32_t* ycnt = ymin + nh; int32_t* yk = ycnt + nh;
+    TRY(vly_resample_coeffs(W, nw, &kh, xmin, xcnt, xk));
+    TRY(vly_resample_coeffs(H, nh, &kv, ymin, ycnt, yk));
+    int row0 = H, row1 = 0;
+    for (int y = cy; y < cy + 224; ++y) {
+      row0 = std::min(row0, ymin[y]);
+      row1 = std::max(row1, ymin[y] + ycnt[y]);
+    }
+    TRY(ensure(c->w_tables, tab.size() * 4));
+    CK(cudaStreamSynchronize(st));           // the previous geometry's tables may still be in use on this stream
+    CK(cudaMemcpy(c->w_tables.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    const int32_t* d = (const int32_t*)c->w_tables.p;
+    p.H = H; p.W = W; p.row0 = row0; p.rows = row1 - row0; p.crop_x = cx; p.crop_y = cy; p.ksize_h = kh; p.ksize_v = kv;
+    p.xmin_h = d; p.cnt_h = d + nw; p.kk_h = d + 2 * (size_t)nw;
+    p.ymin_v = p.kk_h + (size_t)nw * kh; p.cnt_v = p.ymin_v + nh; p.kk_v = p.cnt_v + nh;
+    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f}, sd[3] = {0.26862954f, 0.26130258f, 0.27577711f};   // data_util.py:272-273
+    for (int i = 0; i < 3; ++i) { p.mean[i] = mean[i]; p.std[i] = sd[i]; }
+    c->pre_H = H; c->pre_W = W;
+  }
+  TRY(ensure(c->w_strip, (size_t)T * p.rows * 224 * 3));
+  p.frames = frames; p.T = T; p.strip = (uint8_t*)c->w_strip.p; p.out = out; p.out_dtype = out_dtype;
+  preprocess_horizontal_kernel<<<dim3(p.rows, T), 224, 0, st>>>(p);
+  CKL();
+  if (out_dtype == VLY_F32) preprocess_vertical_kernel<float><<<dim3(224, T), 224, 0, st>>>(p);
+  else if (out_dtype == VLY_F16) preprocess_vertical_kernel<__half><<<dim3(224, T), 224, 0, st>>>(p);
+  else preprocess_vertical_kernel<__nv_bfloat16><<<dim3(224, T), 224, 0, st>>>(p);
+  CKL();
+  c->launches += 2;
   return VLY_OK;
 }
 
