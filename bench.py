@@ -183,13 +183,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="valley2-7b", choices=list(syn.SPECS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--vit-sweep", action="store_true", help="also time ViT encode at F=64 and F=256")
+    ap.add_argument("--vit-sweep", action="store_true", help="also time ViT encode at F = 1 ... 1024 (BASELINE config 5)")
+    ap.add_argument("--batch", type=int, default=1, help="videos per GPU (BASELINE config 3: --model valley-13b --batch 4 --new-tokens 256)")
+    ap.add_argument("--new-tokens", type=int, default=128)
+    ap.add_argument("--frames", type=int, default=8)
     a = ap.parse_args()
+    global N_NEW, N_FRAMES
+    N_NEW, N_FRAMES = a.new_tokens, a.frames
     spec = syn.SPECS[a.model]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    cfg_common = {"workload": f"{a.model}: 1 video x {N_FRAMES} frames 224x224 per GPU, prompt S={1 + 40 + 1 + 256 + 2 + N_FRAMES + 1 + 24}, greedy {N_NEW} new tokens",
-                  "batch_per_gpu": 1, "frames": N_FRAMES, "new_tokens": N_NEW,
+    cfg_common = {"workload": f"{a.model}: {a.batch} video(s) x {N_FRAMES} frames 224x224 per GPU, prompt S={1 + 40 + 1 + 256 + 2 + N_FRAMES + 1 + 24}, greedy {N_NEW} new tokens",
+                  "batch_per_gpu": a.batch, "frames": N_FRAMES, "new_tokens": N_NEW,
                   "parallelism": f"dp{a.gpus} (frames sharded over ranks; frame features gathered by the last ViT GEMM epilogue via NVLink peer stores; LLM replicated)",
                   "l2": "inputs larger than L2 (13.2 GB of weights stream per decode step; ViT weights 606 MB)"}
 
@@ -197,7 +202,7 @@ def main():
         if rank != 0:
             return
         K = max(1, min(a.steps, 2))
-        vals = [cpu_reference_arm(spec) for _ in range(K)]
+        vals = [cpu_reference_arm(spec, N_NEW, N_FRAMES) for _ in range(K)]
         r = vals[-1]
         v = sum(x["tokens_per_s"] for x in vals) / len(vals)
         print(json.dumps({
@@ -226,7 +231,7 @@ def main():
     torch.cuda.synchronize()
     t_load = time.time() - t_load
 
-    n_videos = world                               # weak scaling: one video per GPU
+    n_videos = world * a.batch                     # weak scaling: a.batch videos per GPU
     ids_all = syn.make_prompt_ids(spec, n_videos, N_FRAMES, 0)
     px_all = syn.make_pixels(n_videos, N_FRAMES, 0, dtype=torch.float16)     # callers send fp16 pixels (valley_model.py:430)
     lo, hi = vdist.shard_bounds(n_videos * N_FRAMES, world, rank)
@@ -241,7 +246,7 @@ def main():
     def step_device():
         if world > 1:
             return vdist.generate_sharded(model, ids_dev, px_dev, n_videos, N_FRAMES, N_NEW, fused=fused)
-        return model.generate(input_ids=ids_dev, images=px_dev[None], max_new_tokens=N_NEW)[:, S:]
+        return model.generate(input_ids=ids_dev, images=px_dev.view(a.batch, N_FRAMES, 3, 224, 224), max_new_tokens=N_NEW)[:, S:]
 
     def step_e2e():
         px = px_local_host.cuda(non_blocking=True)
@@ -249,7 +254,7 @@ def main():
         if world > 1:
             out = vdist.generate_sharded(model, ids, px, n_videos, N_FRAMES, N_NEW, fused=fused)
         else:
-            out = model.generate(input_ids=ids, images=px[None], max_new_tokens=N_NEW)[:, S:]
+            out = model.generate(input_ids=ids, images=px.view(a.batch, N_FRAMES, 3, 224, 224), max_new_tokens=N_NEW)[:, S:]
         return out.cpu()
 
     def barrier():
@@ -289,12 +294,12 @@ def main():
     ms_vit8 = vit_only(N_FRAMES)
     sweep = {}
     if a.vit_sweep:
-        for F in (64, 256):
+        for F in (1, 2, 4, 16, 32, 64, 128, 256, 512, 1024):
             sweep[str(F)] = F / (vit_only(F) / 1e3)
 
     def decode_only():
         cache = model.new_cache(vhi - vlo)
-        _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, px_dev[None] if world == 1 else None,
+        _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, px_dev.view(a.batch, N_FRAMES, 3, 224, 224) if world == 1 else None,
                                                                     **({} if world == 1 else dict(frame_features=model.encode_frames(px_dev), n_frames=N_FRAMES)))
         _, nxt = model._prefill(cache, emb, 0)
         import ctypes as C
@@ -395,7 +400,7 @@ def main():
         "tokens_match_e2e": bool(torch.equal(toks.cpu(), toks_e2e)),
     }
     if not a.no_cpu_baseline:
-        r = cpu_reference_arm(spec)
+        r = cpu_reference_arm(spec, N_NEW, N_FRAMES)
         line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                                 "vit_frames_per_s": r["vit_frames_per_s"], "decode_tokens_per_s": r["decode_tokens_per_s"]}
         from oracle import preprocess_oracle as PO          # the reference's PIL pipeline, executed by Pillow (1 core, as load_video runs it)

@@ -1433,8 +1433,15 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   if (n_stages > MegaCfg::MAX_STAGES) n_stages = MegaCfg::MAX_STAGES;
   {
     // measured on B200 (tools/membw.cu): ~96 KB of bulk copies in flight per SM streams at 7.2-7.5 TB/s, 192 KB at 5.2-6 TB/s
+    // A deeper ring with the copies in flight still capped at 3 stages (VLY_MEGA_STAGES=6 VLY_MEGA_INFLIGHT=3) was measured too:
+    // the weight loop shrinks by 0.16 ms/step (the extra slots fill during barriers and the attention phase) but the grid
+    // barriers grow by the same amount -- the critical path is the 48 CTAs that own attention items, not HBM -- so 3 stays.
     static const int want = getenv("VLY_MEGA_STAGES") ? atoi(getenv("VLY_MEGA_STAGES")) : 3;
     if (n_stages > want) n_stages = want;
+  }
+  {
+    static const int inflight = getenv("VLY_MEGA_INFLIGHT") ? atoi(getenv("VLY_MEGA_INFLIGHT")) : 3;
+    p.n_inflight = inflight < 1 ? 1 : (inflight > n_stages ? n_stages : inflight);
   }
   if (n_stages < 2) return fail(VLY_ERR_INVALID, "decode: activations (B=%d, K=%d) leave no room for the weight ring", B, p.Kmax);
   p.n_stages = n_stages;

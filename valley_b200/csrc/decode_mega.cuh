@@ -63,6 +63,7 @@ struct StepParams {
   SampleState* sample;          // token selection state (greedy / temperature sampling, eos bookkeeping); sampling.cuh
   unsigned int* grid_counter;   // zeroed by the host before every launch
   int n_stages;
+  int n_inflight;               // bulk copies outstanding per SM are capped at this many stages (the ring may be deeper)
   long long* dbg;               // optional [gridDim][8] cycle counters: sync, stage-x, weight loop, attention, full-wait
 };
 
@@ -166,6 +167,10 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
+      // The ring is deeper than the number of copies kept in flight: ~96 KB outstanding per SM is what streams fastest
+      // (tools/membw.cu), but while the consumers sit in a grid barrier / stage activations the extra slots keep HBM busy.
+      int wst = 0, issued = 0;
+      uint32_t wph = 0;
       for (int pi = 0; pi < p.n_phases; ++pi) {
         const PhaseDesc& d = p.phases[pi];
         if (d.type == PH_ATTN) continue;
@@ -177,6 +182,11 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
           for (int s = 0; s < n_slices; ++s) {
             const int kc = min(KC, d.K - s * KC);
             mbar_wait(&empty_bar[st], ph ^ 1);
+            if (issued >= p.n_inflight) {                 // copy #(issued - n_inflight) must have landed
+              mbar_wait(&full_bar[wst], wph);
+              if (++wst == p.n_stages) { wst = 0; wph ^= 1; }
+            }
+            ++issued;
             mbar_expect_tx(&full_bar[st], (uint32_t)rows * kc * 2);
             uint8_t* dst = ring + (size_t)st * STAGE_B;
             const __nv_bfloat16* src = d.W + (size_t)n0 * d.K + (size_t)s * KC;
