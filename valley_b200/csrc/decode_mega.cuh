@@ -243,7 +243,9 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         const int n_act = (len + 63) >> 6;
         const int items = p.B * p.nH * n_act;
         const int hl = lane & 15;
-        for (int it = blockIdx.x * 4 + tm; it < items; it += gridDim.x * 4) {
+        // items are dealt team-major: every CTA's team 0 first, so the K/V rows of one layer are requested by as many SMs as
+        // possible (an SM pulls ~50-100 GB/s; four 32 KB items on one SM were the critical path of the phase)
+        for (int it = tm * gridDim.x + blockIdx.x; it < items; it += gridDim.x * 4) {
           const int split = it % n_act, bh = it / n_act;
           const int b = bh / p.nH, h = bh % p.nH;
           const int k0 = split * 64, nk = min(len, k0 + 64) - k0;
@@ -319,14 +321,36 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
           asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
           if (team_flag[tm]) {
             __threadfence();
-            float Mx = -INFINITY;
-            for (int s = 0; s < n_act; ++s) Mx = fmaxf(Mx, __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x));
             float L = 0.f, acc = 0.f;
-            for (int s = 0; s < n_act; ++s) {
-              const float ms = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x), ls = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].y);
-              const float w = ls > 0.f ? fast_exp2(ms - Mx) : 0.f;    // a fully masked split has m = -inf, l = 0
-              L += ls * w;
-              acc += __ldcg(p.part_o + ((size_t)bh * p.nsplit + s) * 128 + tt) * w;
+            if (n_act <= 32) {
+              // the merge sits on the critical path of the phase: one L2 round trip for the (max, sum) pairs -- lane s holds
+              // split s -- and batches of eight independent loads for the partial outputs, instead of 2 n_act dependent ones
+              float ms = -INFINITY, ls = 0.f;
+              if (lane < n_act) {
+                const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane]);
+                ms = ml.x;
+                ls = ml.y;
+              }
+              const float Mx = warp_max(ms);
+              const float wgt = ls > 0.f ? fast_exp2(ms - Mx) : 0.f;          // a fully masked split has m = -inf, l = 0
+              L = warp_sum(ls * wgt);
+              for (int s0 = 0; s0 < n_act; s0 += 8) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  v[j] = (s0 + j < n_act) ? __ldcg(p.part_o + ((size_t)bh * p.nsplit + s0 + j) * 128 + tt) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fmaf(v[j], __shfl_sync(0xffffffffu, wgt, (s0 + j) & 31), acc);
+              }
+            } else {
+              float Mx = -INFINITY;
+              for (int s = 0; s < n_act; ++s) Mx = fmaxf(Mx, __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x));
+              for (int s = 0; s < n_act; ++s) {
+                const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s]);
+                const float w = ml.y > 0.f ? fast_exp2(ml.x - Mx) : 0.f;
+                L += ml.y * w;
+                acc += __ldcg(p.part_o + ((size_t)bh * p.nsplit + s) * 128 + tt) * w;
+              }
             }
             p.attn[(size_t)b * p.H + h * 128 + tt] = __float2bfloat16_rn(L > 0.f ? acc / L : 0.f);
             if (tt == 0) p.attn_counters[bh] = 0;
