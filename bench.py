@@ -220,6 +220,8 @@ def main():
     torch.cuda.set_device(local)
     import torch.distributed as dist
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     from valley_b200 import dist as vdist
     from valley_b200.model import ValleyConfig, ValleyLlamaForCausalLM
