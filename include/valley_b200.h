@@ -52,7 +52,12 @@ typedef struct {
   float vit_eps;
   int32_t mm_vision_select_layer;    /* config.mm_vision_select_layer (default -1, yaml -2; valley_model.py:173) */
   int32_t device;                    /* CUDA device ordinal */
+  int32_t patch_pooling_method;      /* vly_pooling: ValleyLlamaModel.patch_pooling_method (valley_model.py:27, :40-52, :205-213) */
 } vly_config;
+
+/* 'mean' (default), 'max', 'temporal_importance' (config.use_patch_importance_pooling: model.pooling_layer.{weight,bias}),
+ * 'temporal_transformer' (config.use_delta_transformer: model.transformer_delta_encoder.layers.0.* + model.position_matrix) */
+typedef enum { VLY_POOL_MEAN = 0, VLY_POOL_MAX = 1, VLY_POOL_TEMPORAL_IMPORTANCE = 2, VLY_POOL_TEMPORAL_TRANSFORMER = 3 } vly_pooling;
 
 /* Sentinel token ids kept on vision_tower.config by every entry point (run_valley.py:13-18). -1 = unset. */
 typedef struct {
@@ -111,9 +116,11 @@ int vly_preprocess_frames(vly_ctx* ctx, const uint8_t* frames_dev, int T, int H,
  * feats [rows,1024] bf16 -> out [rows,hidden] bf16 */
 int vly_project(vly_ctx* ctx, const void* feats_dev, int64_t rows, void* out_dev, void* stream);
 
-/* ---- temporal mean pool + projector, pool-first (valley_model.py:207, :215 + :190):
+/* ---- temporal pool + projector (valley_model.py:205-215 + :190), per cfg.patch_pooling_method:
  * feats [n_videos*T,257,1024] bf16 -> vis_rows [n_videos, 256+T, hidden] bf16
- * (rows 0..255 = projected mean patch features, rows 256.. = projected per-frame CLS features) */
+ * (rows 0..255 = pooled patch features in LLM space, rows 256.. = projected per-frame CLS features).
+ * mean / temporal_importance pool first and project 256+T rows (the projector is linear and the weights sum to one);
+ * max / temporal_transformer project all 257*T rows and pool in LLM space, as the reference does. */
 int vly_pool_project(vly_ctx* ctx, const void* feats_dev, int n_videos, int T, void* vis_rows_dev, void* stream);
 
 /* ---- splice plan (pure host integer logic, exact; valley_model.py:196-246).  ids_host [B,S] int64.

@@ -59,10 +59,18 @@ def build_reference(spec: syn.ShapeSpec, sd, tmp):
     cfg.mm_hidden_size = spec.vit_hidden
     cfg.mm_vision_select_layer = spec.mm_vision_select_layer
     cfg._attn_implementation = "eager"
+    if spec.patch_pooling_method == "temporal_importance":
+        cfg.use_patch_importance_pooling = True                   # valley_model.py:40-43
+    if spec.patch_pooling_method == "temporal_transformer":
+        cfg.use_delta_transformer = True                          # valley_model.py:45-52
     model = ValleyLlamaForCausalLM(cfg).to(torch.float32).eval()
+    if spec.patch_pooling_method == "max":
+        model.model.patch_pooling_method = "max"                  # only reachable by setting the attribute (:208-209)
     model.model.vision_tower.config._attn_implementation = "eager"
     missing, unexpected = model.load_state_dict(sd, strict=False)
-    bad = [m for m in missing if "post_layernorm" not in m and "position_ids" not in m and "inv_freq" not in m]
+    # transforemr_adding_layer is the template nn.TransformerEncoder deep-copies: present in the state_dict, never executed
+    bad = [m for m in missing if "post_layernorm" not in m and "position_ids" not in m and "inv_freq" not in m
+           and "transforemr_adding_layer" not in m]
     assert not bad and not unexpected, (bad, unexpected)
     vcfg = model.get_model().vision_tower.config
     for k, v in syn.sentinel_ids(spec).items():
@@ -94,7 +102,8 @@ def oracle_cfg(spec):
                           num_attention_heads=spec.num_attention_heads, intermediate_size=spec.intermediate_size,
                           vocab_size=spec.vocab_size, rms_norm_eps=spec.rms_norm_eps, rope_theta=spec.rope_theta,
                           vit_layers=spec.vit_layers, vit_heads=spec.vit_heads, vit_patch=spec.vit_patch,
-                          vit_eps=spec.vit_eps, mm_vision_select_layer=spec.mm_vision_select_layer)
+                          vit_eps=spec.vit_eps, mm_vision_select_layer=spec.mm_vision_select_layer,
+                          patch_pooling_method=spec.patch_pooling_method)
 
 
 def close(a, b, what, rtol=2e-5):
@@ -224,6 +233,39 @@ def main():
                 prefill_logits_last=out.logits[:, -1, :].clone(), prefill_logits_sub=out.logits[:, ::16, ::8].clone(),
                 greedy_tokens=r_tok, greedy_logits=r_log, splice=gold_splice, errors=errs, leftpad=gold_leftpad,
             ), os.path.join(GOLD, f"ref_{spec.name}.pt"))
+            print("  wrote", f"tests/golden/ref_{spec.name}.pt")
+        # --- pooling variants (valley_model.py:205-213): max, temporal_importance (v2), temporal_transformer (v3) -------
+        import transformers
+        for spec in (syn.TINY_MAX, syn.TINY_V2, syn.TINY_V3):
+            print(f"== {spec.name}: patch_pooling_method = {spec.patch_pooling_method}")
+            B, T, seed = 2, 4, 3
+            sd = syn.make_state_dict(spec, seed)
+            ref = build_reference(spec, sd, tmp)
+            assert ref.get_model().patch_pooling_method == spec.patch_pooling_method
+            cfg, tok = oracle_cfg(spec), O.SentinelIds(*[syn.sentinel_ids(spec)[k] for k in (
+                "im_patch_token", "im_start_token", "im_end_token", "vi_frame_token", "vi_start_token", "vi_end_token")])
+            ids, px = syn.make_prompt_ids(spec, B, T, seed), syn.make_pixels(B, T, seed)
+            grabbed, orig = {}, transformers.LlamaModel.forward
+
+            def spy(self, *a, **k):
+                grabbed["e"] = k["inputs_embeds"].clone()
+                return orig(self, *a, **k)
+
+            transformers.LlamaModel.forward = spy
+            try:
+                out = ref(ids, images=px, use_cache=False)
+            finally:
+                transformers.LlamaModel.forward = orig
+            feats = O.encode_images(sd, px, cfg.mm_vision_select_layer, num_layers=cfg.vit_layers)
+            emb = O.prepare_inputs_embeds(sd, ids, feats, tok, spec.patch_pooling_method)
+            close(emb, grabbed["e"], "inputs_embeds after splice")
+            plain = O.prepare_inputs_embeds(sd, ids, feats, tok, "mean")
+            assert (plain - grabbed["e"]).abs().max() > 1e-3          # the variant really differs from mean pooling
+            close(O.causal_lm_forward(sd, cfg, tok, ids, px, None), out.logits, "prefill logits")
+            p0 = (ids[0] == tok.im_start_token).nonzero()[0, 0] + 1
+            torch.save(dict(spec=spec.name, seed=seed, B=B, T=T, pooled_rows=grabbed["e"][:, p0:p0 + 256, :].clone()[:, ::4, ::4],
+                            embeds_sub=grabbed["e"][:, :, ::8].clone(), prefill_logits_last=out.logits[:, -1, :].clone()),
+                       os.path.join(GOLD, f"ref_{spec.name}.pt"))
             print("  wrote", f"tests/golden/ref_{spec.name}.pt")
     print("oracle == reference on all cases; golden fixtures written")
 

@@ -127,14 +127,62 @@ class SentinelIds:
         self.vi_frame_token, self.vi_start_token, self.vi_end_token = vi_frame, vi_start, vi_end
 
 
-def splice_one(ids: Tensor, embeds: Tensor, feat: Tensor, tok: SentinelIds) -> Tensor:
-    """valley_model.py:203-245 for ONE multimodal sample (method 'mean').
+def text_importance_pooling(w: Dict[str, Tensor], patch: Tensor) -> Tensor:
+    """valley_model.py:113-121 ("temporal_importance", config.use_patch_importance_pooling, :40-43):
+    Linear(256*H -> 1) on each frame's flattened patch block, softmax over the T frames, weighted sum.  patch [T,256,H]."""
+    flat = torch.flatten(patch, start_dim=1)
+    score = F.softmax(F.linear(flat, w["model.pooling_layer.weight"], w["model.pooling_layer.bias"]), dim=0)   # [T,1]
+    return torch.sum(score.unsqueeze(2) * patch, dim=0)
 
-    feat [T,257,H]: pooled = mean over T of rows 1: ; frames = row 0 of each frame.
-    Every <im_start> gets the same pooled block (:224-229); the video block is wrapped in a
+
+def temporal_transformer_delta_adding(w: Dict[str, Tensor], patch: Tensor, nhead: int = 8, eps: float = 1e-5) -> Tensor:
+    """valley_model.py:123-133 ("temporal_transformer", config.use_delta_transformer, :45-52): every patch position is a
+    sequence over the T frames; + position_matrix[:T]; ONE post-LN nn.TransformerEncoderLayer(d_model=H, nhead=8,
+    dim_feedforward=2048, relu, batch_first) in eval mode (dropout off); take the LAST frame's output, add the temporal mean.
+    The layer is restated from torch/nn/modules/transformer.py (TransformerEncoderLayer.forward, norm_first=False:
+    x = norm1(x + sa(x)); x = norm2(x + ff(x))) and torch/nn/functional.py multi_head_attention_forward
+    (packed in_proj, q scaled by head_dim**-0.5 before q k^T, softmax, out_proj)."""
+    x = patch.permute(1, 0, 2)                                            # [256,T,H]
+    n, T, H = x.shape
+    pos = w["model.position_matrix"][:T, :].unsqueeze(0).type_as(x)
+    xp = x + pos
+    pfx = "model.transformer_delta_encoder.layers.0."
+    hd = H // nhead
+    qkv = F.linear(xp, w[pfx + "self_attn.in_proj_weight"], w[pfx + "self_attn.in_proj_bias"])
+    q, k, v = [t.view(n, T, nhead, hd).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]   # [256,nhead,T,hd]
+    att = F.softmax(torch.matmul(q * (hd ** -0.5), k.transpose(-1, -2)), dim=-1)
+    a = torch.matmul(att, v).transpose(1, 2).reshape(n, T, H)
+    a = F.linear(a, w[pfx + "self_attn.out_proj.weight"], w[pfx + "self_attn.out_proj.bias"])
+    x1 = F.layer_norm(xp + a, (H,), w[pfx + "norm1.weight"], w[pfx + "norm1.bias"], eps)
+    f = F.linear(F.relu(F.linear(x1, w[pfx + "linear1.weight"], w[pfx + "linear1.bias"])),
+                 w[pfx + "linear2.weight"], w[pfx + "linear2.bias"])
+    x2 = F.layer_norm(x1 + f, (H,), w[pfx + "norm2.weight"], w[pfx + "norm2.bias"], eps)
+    return x2[:, -1, :] + torch.mean(x, dim=1)
+
+
+def pool_patches(w: Dict[str, Tensor], feat: Tensor, method: str = "mean") -> Tensor:
+    """valley_model.py:205-213: the four patch_pooling_method branches on cur_image_features[:,1:,:]  ([T,256,H])."""
+    patch = feat[:, 1:, :]
+    if method == "mean":
+        return torch.mean(patch, dim=0)
+    if method == "max":
+        return torch.max(patch, dim=0)[0]
+    if method == "temporal_importance":
+        return text_importance_pooling(w, patch)
+    if method == "temporal_transformer":
+        return temporal_transformer_delta_adding(w, patch)
+    raise ValueError(method)
+
+
+def splice_one(ids: Tensor, embeds: Tensor, feat: Tensor, tok: SentinelIds, pooled: Optional[Tensor] = None) -> Tensor:
+    """valley_model.py:203-245 for ONE multimodal sample.
+
+    feat [T,257,H]: pooled = the patch_pooling_method over T of rows 1: ('mean' unless given); frames = row 0 of each
+    frame.  Every <im_start> gets the same pooled block (:224-229); the video block is wrapped in a
     bare try/except (:231-244) so ANY failure silently yields the image-only result.
     """
-    pooled = torch.mean(feat[:, 1:, :], dim=0)                            # [256,H]   :207
+    if pooled is None:
+        pooled = torch.mean(feat[:, 1:, :], dim=0)                        # [256,H]   :207
     frames = feat[:, 0, :]                                                # [T,H]     :215
     npatch = pooled.shape[0]
     if (ids == tok.im_start_token).sum() != (ids == tok.im_end_token).sum():
@@ -160,7 +208,8 @@ def splice_one(ids: Tensor, embeds: Tensor, feat: Tensor, tok: SentinelIds) -> T
     return vid
 
 
-def prepare_inputs_embeds(w: Dict[str, Tensor], input_ids: Tensor, image_features, tok: SentinelIds) -> Tensor:
+def prepare_inputs_embeds(w: Dict[str, Tensor], input_ids: Tensor, image_features, tok: SentinelIds,
+                          method: str = "mean") -> Tensor:
     """valley_model.py:155-160 + :192-247.  image_features as returned by encode_images."""
     embeds = F.embedding(input_ids, w["model.embed_tokens.weight"])
     out, cur = [], 0
@@ -168,7 +217,7 @@ def prepare_inputs_embeds(w: Dict[str, Tensor], input_ids: Tensor, image_feature
         if (ids == tok.im_patch_token).sum() == 0:                         # :198-202 (+0*dummy is exactly 0)
             out.append(emb)
             continue
-        out.append(splice_one(ids, emb, image_features[cur], tok))
+        out.append(splice_one(ids, emb, image_features[cur], tok, pool_patches(w, image_features[cur], method)))
         cur += 1
     return torch.stack(out, dim=0)
 
@@ -273,12 +322,13 @@ def llama_model(w: Dict[str, Tensor], inputs_embeds: Tensor, cache: Optional[KVC
 class OracleConfig:
     def __init__(self, *, hidden_size, num_hidden_layers, num_attention_heads, intermediate_size, vocab_size,
                  rms_norm_eps=1e-5, rope_theta=10000.0, vit_layers=24, vit_heads=16, vit_patch=14,
-                 vit_eps=1e-5, mm_vision_select_layer=-2):
+                 vit_eps=1e-5, mm_vision_select_layer=-2, patch_pooling_method="mean"):
         self.hidden_size, self.num_hidden_layers = hidden_size, num_hidden_layers
         self.num_attention_heads, self.intermediate_size = num_attention_heads, intermediate_size
         self.vocab_size, self.rms_norm_eps, self.rope_theta = vocab_size, rms_norm_eps, rope_theta
         self.vit_layers, self.vit_heads, self.vit_patch, self.vit_eps = vit_layers, vit_heads, vit_patch, vit_eps
         self.mm_vision_select_layer = mm_vision_select_layer
+        self.patch_pooling_method = patch_pooling_method
 
 
 def causal_lm_forward(w: Dict[str, Tensor], cfg: OracleConfig, tok: SentinelIds, input_ids: Tensor,
@@ -288,7 +338,7 @@ def causal_lm_forward(w: Dict[str, Tensor], cfg: OracleConfig, tok: SentinelIds,
     if images is not None and input_ids.shape[1] != 1:
         feats = encode_images(w, images, cfg.mm_vision_select_layer, num_layers=cfg.vit_layers,
                               heads=cfg.vit_heads, patch=cfg.vit_patch, eps=cfg.vit_eps)
-        embeds = prepare_inputs_embeds(w, input_ids, feats, tok)
+        embeds = prepare_inputs_embeds(w, input_ids, feats, tok, cfg.patch_pooling_method)
     else:
         embeds = F.embedding(input_ids, w["model.embed_tokens.weight"])
     hidden = llama_model(w, embeds, cache, n_layers=cfg.num_hidden_layers, heads=cfg.num_attention_heads,

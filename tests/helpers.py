@@ -10,7 +10,8 @@ def oracle_cfg(spec):
                           num_attention_heads=spec.num_attention_heads, intermediate_size=spec.intermediate_size,
                           vocab_size=spec.vocab_size, rms_norm_eps=spec.rms_norm_eps, rope_theta=spec.rope_theta,
                           vit_layers=spec.vit_layers, vit_heads=spec.vit_heads, vit_patch=spec.vit_patch,
-                          vit_eps=spec.vit_eps, mm_vision_select_layer=spec.mm_vision_select_layer)
+                          vit_eps=spec.vit_eps, mm_vision_select_layer=spec.mm_vision_select_layer,
+                          patch_pooling_method=spec.patch_pooling_method)
 
 
 def oracle_tok(spec):

@@ -448,6 +448,63 @@ def test_preprocessed_frames_feed_the_vision_tower():
     check_close(got, want, what="ViT on device-preprocessed frames")
 
 
+@pytest.mark.parametrize("spec_name,B,T", [("tiny-max", 2, 4), ("tiny-v2", 2, 4), ("tiny-v3", 2, 4), ("tiny-v2", 1, 8), ("tiny-v3", 3, 1),
+                                            ("shape-7b-1l-v3", 1, 8)])
+def test_pooling_variants_vs_oracle(spec_name, B, T):
+    """patch_pooling_method = max / temporal_importance (v2) / temporal_transformer (v3), valley_model.py:205-213: the spliced
+    inputs_embeds (pooled block + frame rows) and the prefill logits against the oracle; the pooled block must differ from mean pooling."""
+    spec = syn.SPECS[spec_name]
+    big = spec.hidden_size > 1024
+    if big:
+        sd = Hh.bf16_weights(spec, 3)
+        m = Hh.build_model(spec, sd)
+    else:
+        spec, sd, m = get(spec_name, 3)
+    assert m.get_model().patch_pooling_method == spec.patch_pooling_method
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    ids, px = syn.make_prompt_ids(spec, B, T, 3, len_a=10, len_b=6), syn.make_pixels(B, T, 3)
+    with torch.no_grad():
+        feats = O.encode_images(sd, px, cfg.mm_vision_select_layer, num_layers=cfg.vit_layers)
+        want = O.prepare_inputs_embeds(sd, ids, feats, tok, spec.patch_pooling_method)
+        mean = O.prepare_inputs_embeds(sd, ids, feats, tok, "mean")
+        want_logits = O.causal_lm_forward(sd, cfg, tok, ids, px, None)[:, -1]
+    got = m.prepare_inputs_labels_for_multimodal(ids.cuda(), None, None, None, px.cuda())[3]
+    p0 = int((ids[0] == tok.im_start_token).nonzero()[0, 0]) + 1
+    blk = slice(p0, p0 + 256)
+    e = check_close(got[:, blk], want[:, blk], what=f"{spec_name} pooled block")
+    check_close(got, want, what=f"{spec_name} inputs_embeds")
+    if T > 1:
+        assert Hh.rel_fro(got[:, blk], mean[:, blk]) > max(5 * e, 2e-2)          # it is not mean pooling
+    m.logits_all_positions = False
+    try:
+        out = m(input_ids=ids.cuda(), images=px.cuda())
+    finally:
+        m.logits_all_positions = True
+    check_close(out.logits[:, -1], want_logits, what=f"{spec_name} prefill logits")
+    if big:
+        del m
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("spec_name", ["tiny-max", "tiny-v2", "tiny-v3"])
+def test_pooling_variants_golden_reference(spec_name):
+    """The REFERENCE's own outputs with config.use_patch_importance_pooling / use_delta_transformer / patch_pooling_method='max'
+    (tests/golden/ref_tiny-*.pt, written by oracle/make_golden.py from the live valley_model.py)."""
+    g = torch.load(os.path.join(GOLD, f"ref_{spec_name}.pt"))
+    spec = syn.SPECS[spec_name]
+    sd = syn.make_state_dict(spec, g["seed"])
+    m = Hh.build_model(spec, sd)
+    tok = Hh.oracle_tok(spec)
+    ids, px = syn.make_prompt_ids(spec, g["B"], g["T"], g["seed"]), syn.make_pixels(g["B"], g["T"], g["seed"])
+    emb = m.prepare_inputs_labels_for_multimodal(ids.cuda(), None, None, None, px.cuda())[3]
+    p0 = int((ids[0] == tok.im_start_token).nonzero()[0, 0]) + 1
+    assert Hh.rel_fro(emb[:, p0:p0 + 256][:, ::4, ::4], g["pooled_rows"]) < 2e-2
+    assert Hh.rel_fro(emb[:, :, ::8], g["embeds_sub"]) < 2e-2
+    m.logits_all_positions = False
+    out = m(input_ids=ids.cuda(), images=px.cuda())
+    assert Hh.rel_fro(out.logits[:, -1], g["prefill_logits_last"]) < 2e-2
+
+
 def test_cache_capacity_is_enforced():
     spec, sd, m = get("tiny")
     ids = syn.make_prompt_ids(spec, 1, 2, 0)

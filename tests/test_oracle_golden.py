@@ -98,3 +98,19 @@ def test_preprocess_oracle_matches_reference_fixture():
         assert hashlib.sha256(np.ascontiguousarray(f).tobytes()).hexdigest() == g["sha_f32"], (h, w)
         assert np.array_equal(f[:, :, ::9, ::7], g["sub_f32"].numpy())
         assert np.array_equal(P.pil_pipeline(clip), f)                # the Pillow-executed pipeline bench.py times as the CPU baseline
+
+
+@pytest.mark.parametrize("name", ["tiny-max", "tiny-v2", "tiny-v3"])
+def test_oracle_pooling_variants_match_reference_fixture(name):
+    """patch_pooling_method max / temporal_importance / temporal_transformer (valley_model.py:113-133, :205-213)."""
+    g = torch.load(os.path.join(GOLD, f"ref_{name}.pt"))
+    spec = syn.SPECS[name]
+    sd = syn.make_state_dict(spec, g["seed"])
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    ids, px = syn.make_prompt_ids(spec, g["B"], g["T"], g["seed"]), syn.make_pixels(g["B"], g["T"], g["seed"])
+    with torch.no_grad():
+        feats = O.encode_images(sd, px, cfg.mm_vision_select_layer, num_layers=cfg.vit_layers)
+        emb = O.prepare_inputs_embeds(sd, ids, feats, tok, spec.patch_pooling_method)
+        assert torch.allclose(emb[:, :, ::8], g["embeds_sub"], rtol=1e-5, atol=1e-6)
+        logits = O.causal_lm_forward(sd, cfg, tok, ids, px, None)
+        assert torch.allclose(logits[:, -1], g["prefill_logits_last"], rtol=1e-4, atol=1e-5)

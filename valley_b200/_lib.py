@@ -23,6 +23,7 @@ class VlyConfig(C.Structure):
         ("vit_eps", C.c_float),
         ("mm_vision_select_layer", C.c_int32),
         ("device", C.c_int32),
+        ("patch_pooling_method", C.c_int32),
     ]
 
 
@@ -38,6 +39,7 @@ class VlySampling(C.Structure):
 VLY_OK, VLY_ERR_INVALID, VLY_ERR_CUDA, VLY_ERR_STATE = 0, -1, -2, -3
 VLY_ERR_IM_COUNT, VLY_ERR_IM_CUT, VLY_ERR_INDEX = -10, -11, -12
 VLY_F32, VLY_BF16, VLY_F16 = 0, 1, 2
+POOLING = {"mean": 0, "max": 1, "temporal_importance": 2, "temporal_transformer": 3}
 
 # every symbol include/valley_b200.h declares: name -> (restype, argtypes)
 _p, _i, _i64, _vp = C.POINTER, C.c_int, C.c_int64, C.c_void_p

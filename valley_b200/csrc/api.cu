@@ -22,6 +22,7 @@
 #include "decode_kernels.cuh"
 #include "decode_mega.cuh"
 #include "preprocess.cuh"
+#include "pooling_kernels.cuh"
 
 using namespace vly;
 typedef __nv_bfloat16 bf16;
@@ -122,6 +123,14 @@ struct vly_ctx {
   int* g_peer_flags[8] = {};
   int g_world = 0, g_rank = 0, g_epoch = 0;
   Buf w_xlocal;
+  // pooling variants (valley_model.py:40-52, :205-213)
+  float* pool_U = nullptr;                     // temporal_importance: W_proj^T w_pool, [256, vit_hidden] fp32
+  struct DeltaW {                              // temporal_transformer: one post-LN nn.TransformerEncoderLayer + position_matrix
+    bf16 *in_w = nullptr, *out_w = nullptr, *l1_w = nullptr, *l2_w = nullptr, *pos = nullptr;
+    float *in_b = nullptr, *out_b = nullptr, *l1_b = nullptr, *l2_b = nullptr, *n1_g = nullptr, *n1_b = nullptr, *n2_g = nullptr, *n2_b = nullptr;
+    int ffn = 0, max_pos = 0;
+  } delta;
+  Buf w_score, w_pall, w_xp, w_dkv, w_dq, w_datt, w_dx1, w_df1, w_dx2;
   // frame preprocessing: strip + coefficient tables of the last geometry seen
   Buf w_strip, w_tables;
   int pre_H = 0, pre_W = 0;
@@ -595,6 +604,46 @@ extern "C" int vly_finalize_weights(vly_ctx* c) {
       CK(cudaMemcpy(c->proj_w, pjw, (size_t)g.hidden_size * D * 2, cudaMemcpyDeviceToDevice));
       CK(cudaMemcpy(c->proj_b, pjb, g.hidden_size * 4, cudaMemcpyDeviceToDevice));
       drop_staged(c, "model.mm_projector.weight");
+      const int H = g.hidden_size, NP = (g.vit_image / g.vit_patch) * (g.vit_image / g.vit_patch);
+      if (g.patch_pooling_method == VLY_POOL_TEMPORAL_IMPORTANCE) {       // valley_model.py:40-43
+        void* pw;
+        TRY(get_staged(c, "model.pooling_layer.weight", false, (int64_t)NP * H, &pw));
+        TRY(dalloc(c, &c->pool_U, (size_t)NP * D));
+        fold_importance_kernel<<<NP, 256>>>((const bf16*)pw, c->proj_w, c->pool_U, H, D);      // the bias cancels in the softmax
+        CKL();
+        CK(cudaDeviceSynchronize());
+        drop_staged(c, "model.pooling_layer.weight");
+      } else if (g.patch_pooling_method == VLY_POOL_TEMPORAL_TRANSFORMER) {   // valley_model.py:45-52
+        const std::string q = "model.transformer_delta_encoder.layers.0.";
+        vly_ctx::DeltaW& w = c->delta;
+        auto it = c->staged.find(q + "linear1.weight");
+        if (it == c->staged.end()) return fail(VLY_ERR_STATE, "vly_finalize_weights: missing tensor '%slinear1.weight'", q.c_str());
+        w.ffn = (int)(it->second.numel / H);
+        auto ip = c->staged.find("model.position_matrix");
+        if (ip == c->staged.end()) return fail(VLY_ERR_STATE, "vly_finalize_weights: missing tensor 'model.position_matrix'");
+        w.max_pos = (int)(ip->second.numel / H);
+        struct { const char* name; bool f32; int64_t n; void** dst; } items[] = {
+            {"self_attn.in_proj_weight", false, (int64_t)3 * H * H, (void**)&w.in_w}, {"self_attn.in_proj_bias", true, 3 * H, (void**)&w.in_b},
+            {"self_attn.out_proj.weight", false, (int64_t)H * H, (void**)&w.out_w},   {"self_attn.out_proj.bias", true, H, (void**)&w.out_b},
+            {"linear1.weight", false, (int64_t)w.ffn * H, (void**)&w.l1_w},           {"linear1.bias", true, w.ffn, (void**)&w.l1_b},
+            {"linear2.weight", false, (int64_t)H * w.ffn, (void**)&w.l2_w},           {"linear2.bias", true, H, (void**)&w.l2_b},
+            {"norm1.weight", true, H, (void**)&w.n1_g}, {"norm1.bias", true, H, (void**)&w.n1_b},
+            {"norm2.weight", true, H, (void**)&w.n2_g}, {"norm2.bias", true, H, (void**)&w.n2_b}};
+        for (auto& it2 : items) {
+          void* src;
+          TRY(get_staged(c, q + it2.name, it2.f32, it2.n, &src));
+          const size_t bytes = (size_t)it2.n * (it2.f32 ? 4 : 2);
+          CK(cudaMalloc(it2.dst, bytes));
+          c->owned.push_back(*it2.dst);
+          CK(cudaMemcpy(*it2.dst, src, bytes, cudaMemcpyDeviceToDevice));
+          drop_staged(c, q + it2.name);
+        }
+        void* pm;
+        TRY(get_staged(c, "model.position_matrix", false, (int64_t)w.max_pos * H, &pm));
+        TRY(dalloc(c, &w.pos, (size_t)w.max_pos * H));
+        CK(cudaMemcpy(w.pos, pm, (size_t)w.max_pos * H * 2, cudaMemcpyDeviceToDevice));
+        drop_staged(c, "model.position_matrix");
+      }
     }
   }
 
@@ -933,6 +982,77 @@ extern "C" int vly_project(vly_ctx* c, const void* feats, int64_t rows, void* ou
   return launch_gemm<EPI_BIAS>(c, pick_bn(p.N), (const bf16*)feats, p.K, c->proj_w, p.K, p, (cudaStream_t)stream);
 }
 
+// 'max' and 'temporal_transformer' act on the PROJECTED tokens (they do not commute with the projector): project all
+// T*257 rows of one video at a time, then pool.  valley_model.py:208-209, :123-133.
+static int pool_project_after(vly_ctx* c, const bf16* feats, int n_videos, int T, bf16* vis_rows, cudaStream_t st) {
+  const vly_config& g = c->cfg;
+  const int D = g.vit_hidden, H = g.hidden_size, tokens = (g.vit_image / g.vit_patch) * (g.vit_image / g.vit_patch) + 1;
+  const int NP = tokens - 1, rows_out = NP + T, nhead = 8;
+  const vly_ctx::DeltaW& w = c->delta;
+  const bool tr = g.patch_pooling_method == VLY_POOL_TEMPORAL_TRANSFORMER;
+  if (tr) {
+    if (!w.in_w) return fail(VLY_ERR_STATE, "vly_pool_project: transformer_delta_encoder weights not loaded");
+    if (T > 64 || T > w.max_pos) return fail(VLY_ERR_INVALID, "vly_pool_project: temporal transformer supports at most %d frames (got %d)", w.max_pos < 64 ? w.max_pos : 64, T);
+    if ((H / nhead) % 64) return fail(VLY_ERR_INVALID, "vly_pool_project: hidden_size / 8 must be a multiple of 64");
+  }
+  TRY(ensure(c->w_pall, (size_t)T * tokens * H * 2));
+  if (tr) {
+    TRY(ensure(c->w_xp, (size_t)T * NP * H * 2));
+    TRY(ensure(c->w_dkv, (size_t)T * NP * 2 * H * 2));
+    TRY(ensure(c->w_dq, (size_t)NP * H * 2));
+    TRY(ensure(c->w_datt, (size_t)NP * H * 2));
+    TRY(ensure(c->w_dx1, (size_t)NP * H * 2));
+    TRY(ensure(c->w_df1, (size_t)NP * w.ffn * 2));
+    TRY(ensure(c->w_dx2, (size_t)NP * H * 2));
+  }
+  bf16* P = (bf16*)c->w_pall.p;
+  for (int v = 0; v < n_videos; ++v) {
+    bf16* vis = vis_rows + (size_t)v * rows_out * H;
+    {  // mm_projector over every token of the video (valley_model.py:187-190)
+      GemmParams p = {};
+      p.M = T * tokens; p.N = H; p.K = D; p.out = P; p.ldo = H; p.bias = c->proj_b;
+      TRY(launch_gemm<EPI_BIAS>(c, pick_bn_m(c, H, p.M), feats + (size_t)v * T * tokens * D, D, c->proj_w, D, p, st));
+    }
+    if (!tr) {
+      temporal_max_kernel<<<148 * 2, 256, 0, st>>>(P, vis, T, tokens, H);
+      c->launches++;
+      CKL();
+      continue;
+    }
+    bf16 *Xp = (bf16*)c->w_xp.p, *KV = (bf16*)c->w_dkv.p, *Q = (bf16*)c->w_dq.p, *att = (bf16*)c->w_datt.p;
+    bf16 *X1 = (bf16*)c->w_dx1.p, *F1 = (bf16*)c->w_df1.p, *X2 = (bf16*)c->w_dx2.p;
+    const bf16* Xlast = Xp + (size_t)(T - 1) * NP * H;          // rows of the last frame: the only queries that are used (:130)
+    delta_add_pos_kernel<<<148 * 2, 256, 0, st>>>(P, w.pos, Xp, T, tokens, H);
+    c->launches++;
+    GemmParams p = {};
+    p.M = T * NP; p.N = 2 * H; p.K = H; p.out = KV; p.ldo = 2 * H; p.bias = w.in_b + H;          // k | v rows of in_proj
+    TRY(launch_gemm<EPI_BIAS>(c, pick_bn_m(c, p.N, p.M), Xp, H, w.in_w + (size_t)H * H, H, p, st));
+    p = {};
+    p.M = NP; p.N = H; p.K = H; p.out = Q; p.ldo = H; p.bias = w.in_b;
+    TRY(launch_gemm<EPI_BIAS>(c, pick_bn_m(c, p.N, p.M), Xlast, H, w.in_w, H, p, st));
+    delta_attention_kernel<<<NP, nhead * 32, 0, st>>>(Q, KV, att, T, NP, H, nhead);
+    c->launches++;
+    p = {};
+    p.M = NP; p.N = H; p.K = H; p.out = X1; p.ldo = H; p.bias = w.out_b; p.residual = Xlast; p.ldr = H;
+    TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, pick_bn_m(c, p.N, p.M), att, H, w.out_w, H, p, st));
+    layernorm_rows_kernel<<<NP, 256, 0, st>>>(X1, w.n1_g, w.n1_b, X1, H, 1e-5f);
+    c->launches++;
+    p = {};
+    p.M = NP; p.N = w.ffn; p.K = H; p.out = F1; p.ldo = w.ffn; p.bias = w.l1_b;
+    TRY(launch_gemm<EPI_BIAS>(c, pick_bn_m(c, p.N, p.M), X1, H, w.l1_w, H, p, st));
+    relu_inplace_kernel<<<148, 256, 0, st>>>(F1, (long long)NP * w.ffn / 8);
+    c->launches++;
+    p = {};
+    p.M = NP; p.N = H; p.K = w.ffn; p.out = X2; p.ldo = H; p.bias = w.l2_b; p.residual = X1; p.ldr = H;
+    TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, pick_bn_m(c, p.N, p.M), F1, w.ffn, w.l2_w, w.ffn, p, st));
+    layernorm_rows_kernel<<<NP, 256, 0, st>>>(X2, w.n2_g, w.n2_b, X2, H, 1e-5f);
+    delta_finish_kernel<<<148 * 2, 256, 0, st>>>(P, X2, vis, T, tokens, H);
+    c->launches += 2;
+    CKL();
+  }
+  return VLY_OK;
+}
+
 extern "C" int vly_pool_project(vly_ctx* c, const void* feats, int n_videos, int T, void* vis_rows, void* stream) {
   if (!c || !feats || !vis_rows || n_videos <= 0 || T <= 0) return fail(VLY_ERR_INVALID, "vly_pool_project: bad argument");
   std::lock_guard<std::mutex> lk(c->mu);
@@ -942,8 +1062,19 @@ extern "C" int vly_pool_project(vly_ctx* c, const void* feats, int n_videos, int
   const vly_config& g = c->cfg;
   const int D = g.vit_hidden, tokens = (g.vit_image / g.vit_patch) * (g.vit_image / g.vit_patch) + 1;
   const int rows = tokens - 1 + T;
+  if (g.patch_pooling_method == VLY_POOL_MAX || g.patch_pooling_method == VLY_POOL_TEMPORAL_TRANSFORMER)
+    return pool_project_after(c, (const bf16*)feats, n_videos, T, (bf16*)vis_rows, st);
   TRY(ensure(c->w_pool, (size_t)n_videos * rows * D * 2));
-  temporal_pool_kernel<<<148 * 4, 256, 0, st>>>((const bf16*)feats, (bf16*)c->w_pool.p, n_videos, T, tokens, D);
+  if (g.patch_pooling_method == VLY_POOL_TEMPORAL_IMPORTANCE) {
+    // softmax_t(w . flatten(proj(x_t))) weights: scores straight from the ViT features through the folded U (pooling_kernels.cuh)
+    if (!c->pool_U) return fail(VLY_ERR_STATE, "vly_pool_project: model.pooling_layer.weight not loaded");
+    TRY(ensure(c->w_score, (size_t)n_videos * T * 4));
+    importance_score_kernel<<<dim3(T, n_videos), 256, 0, st>>>((const bf16*)feats, c->pool_U, (float*)c->w_score.p, T, tokens, D);
+    weighted_pool_kernel<<<148 * 4, 256, 0, st>>>((const bf16*)feats, (const float*)c->w_score.p, (bf16*)c->w_pool.p, n_videos, T, tokens, D);
+    c->launches++;
+  } else {
+    temporal_pool_kernel<<<148 * 4, 256, 0, st>>>((const bf16*)feats, (bf16*)c->w_pool.p, n_videos, T, tokens, D);
+  }
   c->launches++;
   CKL();
   GemmParams p = {};

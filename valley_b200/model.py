@@ -44,14 +44,17 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 class ValleyConfig:
     """ValleyConfig(LlamaConfig), model_type 'valley' (valley_model.py:18-19) plus the extra keys the reference
-    reads: mm_vision_tower, use_mm_proj, mm_hidden_size, mm_vision_select_layer, mm_use_im_start_end."""
+    reads: mm_vision_tower, use_mm_proj, mm_hidden_size, mm_vision_select_layer, mm_use_im_start_end,
+    use_patch_importance_pooling / use_delta_transformer (:40-52; the pooling variant is fixed at construction, as in the
+    reference -- ``patch_pooling_method="max"`` stands for setting that attribute on the reference model)."""
     model_type = "valley"
 
     def __init__(self, hidden_size=4096, num_hidden_layers=32, num_attention_heads=32, intermediate_size=11008,
                  vocab_size=32008, rms_norm_eps=1e-5, rope_theta=10000.0, max_position_embeddings=2048,
                  mm_vision_tower="openai/clip-vit-large-patch14", mm_hidden_size=1024, mm_vision_select_layer=-2,
                  use_mm_proj=True, mm_use_im_start_end=True, vit_layers=24, vit_heads=16, vit_mlp=4096, vit_patch=14,
-                 vit_image=224, vit_eps=1e-5, **kw):
+                 vit_image=224, vit_eps=1e-5, use_patch_importance_pooling=False, use_delta_transformer=False,
+                 patch_pooling_method=None, **kw):
         self.hidden_size, self.num_hidden_layers = hidden_size, num_hidden_layers
         self.num_attention_heads, self.intermediate_size = num_attention_heads, intermediate_size
         self.vocab_size, self.rms_norm_eps, self.rope_theta = vocab_size, rms_norm_eps, rope_theta
@@ -61,6 +64,13 @@ class ValleyConfig:
         self.mm_use_im_start_end = mm_use_im_start_end
         self.vit_layers, self.vit_heads, self.vit_mlp = vit_layers, vit_heads, vit_mlp
         self.vit_patch, self.vit_image, self.vit_eps = vit_patch, vit_image, vit_eps
+        self.use_patch_importance_pooling, self.use_delta_transformer = use_patch_importance_pooling, use_delta_transformer
+        if patch_pooling_method is None:          # valley_model.py:27, :40-52: the later flag wins
+            patch_pooling_method = "temporal_transformer" if use_delta_transformer else (
+                "temporal_importance" if use_patch_importance_pooling else "mean")
+        if patch_pooling_method not in _lib.POOLING:
+            raise ValueError(f"patch_pooling_method {patch_pooling_method!r} not in {sorted(_lib.POOLING)}")
+        self.patch_pooling_method = patch_pooling_method
         self.use_return_dict, self.use_cache = True, True
         self.output_attentions = self.output_hidden_states = False
         for k, v in kw.items():
@@ -74,7 +84,8 @@ class ValleyConfig:
                    max_position_embeddings=spec.max_position_embeddings, mm_hidden_size=spec.vit_hidden,
                    mm_vision_select_layer=spec.mm_vision_select_layer, vit_layers=spec.vit_layers,
                    vit_heads=spec.vit_heads, vit_mlp=spec.vit_mlp, vit_patch=spec.vit_patch,
-                   vit_image=spec.vit_image, vit_eps=spec.vit_eps, **kw)
+                   vit_image=spec.vit_image, vit_eps=spec.vit_eps,
+                   patch_pooling_method=getattr(spec, "patch_pooling_method", "mean"), **kw)
 
 
 class CausalLMOutputWithPast(dict):
@@ -182,7 +193,7 @@ class ValleyLlamaModel:
         self._owner = owner
         self.config = owner.config
         self.vision_tower = _VisionTower(owner)
-        self.patch_pooling_method = "mean"          # valley_model.py:27
+        self.patch_pooling_method = owner.config.patch_pooling_method      # valley_model.py:27, :40-52
         self.mm_projector = types.SimpleNamespace(in_features=owner.config.mm_hidden_size,
                                                   out_features=owner.config.hidden_size)
         self.embed_tokens = types.SimpleNamespace(num_embeddings=owner.config.vocab_size,
@@ -205,7 +216,8 @@ class ValleyLlamaForCausalLM:
         c = VlyConfig(config.hidden_size, config.num_hidden_layers, config.num_attention_heads, config.intermediate_size,
                       config.vocab_size, config.rms_norm_eps, config.rope_theta, config.max_position_embeddings,
                       config.mm_hidden_size, config.vit_layers, config.vit_heads, config.vit_mlp, config.vit_patch,
-                      config.vit_image, config.vit_eps, config.mm_vision_select_layer, dev.index or 0)
+                      config.vit_image, config.vit_eps, config.mm_vision_select_layer, dev.index or 0,
+                      _lib.POOLING[config.patch_pooling_method])
         h = C.c_void_p()
         check(self._lib.vly_create(C.byref(c), C.byref(h)))
         self._ctx = h
@@ -236,6 +248,8 @@ class ValleyLlamaForCausalLM:
         items = state.items() if hasattr(state, "items") else state
         for name, t in items:
             if "post_layernorm" in name or name.endswith("position_ids") or name.endswith("inv_freq"):
+                continue
+            if "transforemr_adding_layer" in name:      # the template nn.TransformerEncoder deep-copies; never executed (valley_model.py:47-48)
                 continue
             t = t.detach()
             if t.dtype not in _DT:

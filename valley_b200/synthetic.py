@@ -37,6 +37,7 @@ class ShapeSpec:
     vit_image: int = 224
     vit_eps: float = 1e-5
     mm_vision_select_layer: int = -2
+    patch_pooling_method: str = "mean"   # "mean" | "max" | "temporal_importance" (v2) | "temporal_transformer" (v3)
 
 
 VALLEY2_7B = ShapeSpec("valley2-7b", 4096, 32, 32, 11008, rms_norm_eps=1e-5)          # Llama-2-7B shape
@@ -48,7 +49,14 @@ TINY_WIDE = ShapeSpec("tiny-wide", 768, 3, 6, 1536, vocab_size=2056, vit_layers=
 SHAPE_7B_1L = ShapeSpec("shape-7b-1l", 4096, 1, 32, 11008, vit_layers=2)
 SHAPE_13B_1L = ShapeSpec("shape-13b-1l", 5120, 1, 40, 13824, rms_norm_eps=1e-6, vit_layers=2)
 
-SPECS = {s.name: s for s in (VALLEY2_7B, VALLEY_13B, TINY, TINY_WIDE, SHAPE_7B_1L, SHAPE_13B_1L)}
+# pooling variants (valley_model.py:40-52): v2 = learned temporal importance, v3 = temporal transformer delta
+TINY_V2 = ShapeSpec("tiny-v2", 512, 2, 4, 1024, vocab_size=1032, vit_layers=2, patch_pooling_method="temporal_importance")
+TINY_V3 = ShapeSpec("tiny-v3", 512, 2, 4, 1024, vocab_size=1032, vit_layers=2, patch_pooling_method="temporal_transformer")
+TINY_MAX = ShapeSpec("tiny-max", 512, 2, 4, 1024, vocab_size=1032, vit_layers=2, patch_pooling_method="max")
+SHAPE_7B_1L_V3 = ShapeSpec("shape-7b-1l-v3", 4096, 1, 32, 11008, vit_layers=2, patch_pooling_method="temporal_transformer")
+
+SPECS = {s.name: s for s in (VALLEY2_7B, VALLEY_13B, TINY, TINY_WIDE, SHAPE_7B_1L, SHAPE_13B_1L, TINY_V2, TINY_V3, TINY_MAX,
+                             SHAPE_7B_1L_V3)}
 
 
 def weight_shapes(spec: ShapeSpec, *, vision: bool = True, llm: bool = True) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
@@ -77,6 +85,24 @@ def weight_shapes(spec: ShapeSpec, *, vision: bool = True, llm: bool = True) -> 
             yield q + "layer_norm2.bias", (D,), "ln_b"
         yield "model.mm_projector.weight", (H, D), "lin"
         yield "model.mm_projector.bias", (H,), "bias"
+        if spec.patch_pooling_method == "temporal_importance":          # valley_model.py:40-43
+            yield "model.pooling_layer.weight", (1, H * 256), "pool"
+            yield "model.pooling_layer.bias", (1,), "bias"
+        if spec.patch_pooling_method == "temporal_transformer":         # valley_model.py:45-52
+            q = "model.transformer_delta_encoder.layers.0."
+            yield "model.position_matrix", (2048, H), "emb"
+            yield q + "self_attn.in_proj_weight", (3 * H, H), "lin"
+            yield q + "self_attn.in_proj_bias", (3 * H,), "bias"
+            yield q + "self_attn.out_proj.weight", (H, H), "lin"
+            yield q + "self_attn.out_proj.bias", (H,), "bias"
+            yield q + "linear1.weight", (2048, H), "lin"
+            yield q + "linear1.bias", (2048,), "bias"
+            yield q + "linear2.weight", (H, 2048), "lin_out"
+            yield q + "linear2.bias", (H,), "bias"
+            yield q + "norm1.weight", (H,), "ln_w"
+            yield q + "norm1.bias", (H,), "ln_b"
+            yield q + "norm2.weight", (H,), "ln_w"
+            yield q + "norm2.bias", (H,), "ln_b"
     if llm:
         yield "model.embed_tokens.weight", (V, H), "tok"
         for i in range(spec.num_hidden_layers):
@@ -102,6 +128,8 @@ def _init(kind: str, shape, gen: torch.Generator, device, fan_in: int) -> torch.
         return r * 0.05
     if kind == "tok":
         return r * 0.5
+    if kind == "pool":
+        return r * 0.002          # scores = w . flatten(256*H features): keeps the softmax over frames informative
     if kind == "emb":
         return r * 0.02
     if kind == "bias":
