@@ -166,6 +166,12 @@ int vly_llama_decode(vly_ctx* ctx, vly_kv* kv, const int64_t* tokens_dev, int64_
 int vly_generate_greedy(vly_ctx* ctx, vly_kv* kv, const int64_t* first_tokens_dev, int n_steps, int64_t* out_tokens_dev,
                         void* stream);
 
+/* ---- loss of a forward with labels (valley_model.py:308-318): shift by one, CrossEntropyLoss() = mean of
+ * logsumexp(logits[b,s,:]) - logits[b,s,labels[b,s+1]] over the labels != ignore_index (-100).  logits_dev [B,S,V] fp32
+ * (vly_llama_prefill logits_mode 2), labels_dev [B,S] int64, loss_out_dev one fp32 (nan when no label counts, like torch). */
+int vly_cross_entropy(vly_ctx* ctx, const float* logits_dev, const int64_t* labels_dev, int B, int S, int64_t ignore_index,
+                      float* loss_out_dev, void* stream);
+
 /* ---- token selection on the device (model_worker.py:388-397; HF generate as called at valley_model.py:432) ----
  * temperature < 1e-4: arg-max (model_worker.py:390-391); otherwise multinomial(softmax(logits / temperature)) (:392-395), drawn
  * with the Gumbel-max identity from counter-based Philox noise keyed by `seed` -- fused into the arg-max epilogue of the decode

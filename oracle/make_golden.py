@@ -166,6 +166,13 @@ def main():
                 close(mo, o.logits, f"left-pad decode step {i} logits")
                 lp_steps.append(o.logits[:, -1].clone())
                 cur = o.logits[:, -1].argmax(-1)[:, None]
+            # --- labels -> loss (valley_model.py:308-318), prompt part masked with IGNORE_INDEX like the data pipeline ------
+            labels = ids.clone()
+            labels[:, : ids.shape[1] // 2] = -100
+            lo = ref(ids, images=px, labels=labels, use_cache=False)
+            mine_loss = O.causal_lm_loss(O.causal_lm_forward(sd, cfg, tok, ids, px, None), labels)
+            close(mine_loss[None], lo.loss[None], "cross-entropy loss (labels)")
+            gold_loss = dict(labels=labels, loss=lo.loss.clone())
             gold_leftpad = dict(ids=ids_p, mask=am, prefill_logits_last=lp_out.logits[:, -1].clone(), first_token=lp_first,
                                 decode_logits=torch.stack(lp_steps, 1))
 
@@ -231,7 +238,7 @@ def main():
                 spec=spec.name, seed=seed, B=B, T=T,
                 vit_hidden_m2_sub=hs[-2][:, ::4, ::8].clone(), vit_hidden_m1_sub=hs[-1][:, ::4, ::8].clone(),
                 prefill_logits_last=out.logits[:, -1, :].clone(), prefill_logits_sub=out.logits[:, ::16, ::8].clone(),
-                greedy_tokens=r_tok, greedy_logits=r_log, splice=gold_splice, errors=errs, leftpad=gold_leftpad,
+                greedy_tokens=r_tok, greedy_logits=r_log, splice=gold_splice, errors=errs, leftpad=gold_leftpad, loss=gold_loss,
             ), os.path.join(GOLD, f"ref_{spec.name}.pt"))
             print("  wrote", f"tests/golden/ref_{spec.name}.pt")
         # --- pooling variants (valley_model.py:205-213): max, temporal_importance (v2), temporal_transformer (v3) -------

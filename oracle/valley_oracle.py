@@ -368,3 +368,12 @@ def greedy_generate(w: Dict[str, Tensor], cfg: OracleConfig, tok: SentinelIds, i
         cur = nxt[:, None]
     out = torch.stack(tokens, dim=1)
     return (out, torch.stack(all_logits, dim=1)) if return_logits else out
+
+
+def causal_lm_loss(logits: Tensor, labels: Tensor, ignore_index: int = -100) -> Tensor:
+    """valley_model.py:308-318: shift (tokens < n predict n), flatten, nn.CrossEntropyLoss() -- mean over the labels that are
+    not ignore_index (-100, the IGNORE_INDEX the data pipeline writes over the prompt part)."""
+    V = logits.shape[-1]
+    sl = logits[..., :-1, :].contiguous().view(-1, V)
+    tl = labels[..., 1:].contiguous().view(-1)
+    return F.cross_entropy(sl, tl, ignore_index=ignore_index)

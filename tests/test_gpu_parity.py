@@ -505,6 +505,27 @@ def test_pooling_variants_golden_reference(spec_name):
     assert Hh.rel_fro(out.logits[:, -1], g["prefill_logits_last"]) < 2e-2
 
 
+def test_forward_with_labels_returns_the_reference_loss():
+    """valley_model.py:308-318 through vly_cross_entropy: oracle on the same weights, and the REFERENCE's fp32 loss (golden)."""
+    spec, sd, m = get("tiny")
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    g = torch.load(os.path.join(GOLD, "ref_tiny.pt"))
+    ids, px = syn.make_prompt_ids(spec, g["B"], g["T"], g["seed"]), syn.make_pixels(g["B"], g["T"], g["seed"])
+    labels = g["loss"]["labels"]
+    with torch.no_grad():
+        want = O.causal_lm_loss(O.causal_lm_forward(sd, cfg, tok, ids, px, None), labels)
+    out = m(input_ids=ids.cuda(), images=px.cuda(), labels=labels.cuda())
+    assert abs(float(out.loss) - float(want)) < 2e-2 * float(want), (float(out.loss), float(want))
+    assert abs(float(out.loss) - float(g["loss"]["loss"])) < 2e-2 * float(want)
+    # exactly the mean of logsumexp - logit[label] over the counted labels of OUR logits (fp32 arithmetic check of the kernel)
+    mine = torch.nn.functional.cross_entropy(out.logits[:, :-1].reshape(-1, spec.vocab_size).cpu().double(), labels[:, 1:].reshape(-1))
+    assert abs(float(out.loss) - float(mine)) < 1e-5 * float(mine)
+    tup = m(input_ids=ids.cuda(), images=px.cuda(), labels=labels.cuda(), return_dict=False)
+    assert len(tup) == 3 and float(tup[0]) == float(out.loss)
+    allign = m(input_ids=ids.cuda(), images=px.cuda(), labels=torch.full_like(labels, -100).cuda())
+    assert torch.isnan(allign.loss)                                  # nothing counted: nan, like nn.CrossEntropyLoss
+
+
 def test_cache_capacity_is_enforced():
     spec, sd, m = get("tiny")
     ids = syn.make_prompt_ids(spec, 1, 2, 0)

@@ -114,3 +114,16 @@ def test_oracle_pooling_variants_match_reference_fixture(name):
         assert torch.allclose(emb[:, :, ::8], g["embeds_sub"], rtol=1e-5, atol=1e-6)
         logits = O.causal_lm_forward(sd, cfg, tok, ids, px, None)
         assert torch.allclose(logits[:, -1], g["prefill_logits_last"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny-wide"])
+def test_oracle_loss_matches_reference_fixture(name):
+    """forward(labels=...) -> shifted cross-entropy with IGNORE_INDEX (valley_model.py:308-318)."""
+    g = torch.load(os.path.join(GOLD, f"ref_{name}.pt"))
+    spec = syn.SPECS[name]
+    sd = syn.make_state_dict(spec, g["seed"])
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    ids, px = syn.make_prompt_ids(spec, g["B"], g["T"], g["seed"]), syn.make_pixels(g["B"], g["T"], g["seed"])
+    with torch.no_grad():
+        loss = O.causal_lm_loss(O.causal_lm_forward(sd, cfg, tok, ids, px, None), g["loss"]["labels"])
+    assert torch.allclose(loss, g["loss"]["loss"], rtol=1e-5, atol=1e-6)

@@ -71,6 +71,7 @@ SIGNATURES = {
     "vly_llama_prefill": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "vly_llama_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "vly_generate_greedy": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "vly_cross_entropy": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp]),
     "vly_sample_logits": (_i, [_vp, _vp, _vp, _p(VlySampling), _vp, _vp]),
     "vly_generate": (_i, [_vp, _vp, _vp, _i, _vp, _p(VlySampling), _vp, _vp]),
     "vly_kernel_launch_count": (_i, [_vp, _p(_i64)]),

@@ -1737,6 +1737,26 @@ extern "C" int vly_llama_decode(vly_ctx* c, vly_kv* kv, const int64_t* tokens, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// shifted cross-entropy over [B,S,V] logits (valley_model.py:308-318)
+// ------------------------------------------------------------------------------------------------
+extern "C" int vly_cross_entropy(vly_ctx* c, const float* logits, const int64_t* labels, int B, int S, int64_t ignore_index, float* loss_out,
+                                 void* stream) {
+  if (!c || !logits || !labels || !loss_out || B <= 0 || S < 2) return fail(VLY_ERR_INVALID, "vly_cross_entropy: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = B * (S - 1);
+  TRY(ensure(c->w_score, (size_t)rows * 8));
+  float* nll = (float*)c->w_score.p;
+  int* cnt = (int*)(nll + rows);
+  ce_rows_kernel<<<rows, 256, 0, st>>>(logits, (const long long*)labels, S, c->cfg.vocab_size, ignore_index, nll, cnt);
+  ce_mean_kernel<<<1, 1024, 0, st>>>(nll, cnt, rows, loss_out);
+  c->launches += 2;
+  CKL();
+  return VLY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // frame preprocessing (load_video's Resize(256) -> CenterCrop(224) -> /255 -> CLIP mean/std), SURVEY 8 f-2
 // ------------------------------------------------------------------------------------------------
 extern "C" int vly_preprocess_frames(vly_ctx* c, const uint8_t* frames, int T, int H, int W, int out_dtype, void* out, void* stream) {

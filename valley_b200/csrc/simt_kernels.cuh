@@ -558,6 +558,66 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnPara
   }
 }
 
+// ============================================================================================
+// Shifted cross-entropy (valley_model.py:308-318): row r = (b, s) with s < S-1 scores logits[b, s, :] against labels[b, s+1];
+// nll = logsumexp - logit[label]; labels == ignore_index are skipped; loss = mean over the counted rows.
+// grid (B*(S-1)), 256 threads -> nll[r] (0 when ignored), cnt[r]; ce_mean_kernel folds them in a fixed order (deterministic).
+// ============================================================================================
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int S, int V,
+                                                      long long ignore_index, float* __restrict__ nll, int* __restrict__ cnt) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int r = blockIdx.x, b = r / (S - 1), s = r % (S - 1);
+  const long long lab = labels[(size_t)b * S + s + 1];
+  if (lab == ignore_index || lab < 0 || lab >= V) {
+    if (threadIdx.x == 0) { nll[r] = 0.f; cnt[r] = 0; }
+    return;
+  }
+  const float* x = logits + ((size_t)b * S + s) * V;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += 256) m = fmaxf(m, x[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+    bc = t;
+  }
+  __syncthreads();
+  m = bc;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < V; i += 256) sum += expf(x[i] - m);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    nll[r] = m + logf(t) - x[lab];
+    cnt[r] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(1024) ce_mean_kernel(const float* __restrict__ nll, const int* __restrict__ cnt, int rows, float* __restrict__ loss) {
+  __shared__ double sv[32];
+  __shared__ int sc[32];
+  double a = 0.0;
+  int c = 0;
+  for (int i = threadIdx.x; i < rows; i += 1024) { a += nll[i]; c += cnt[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = a; sc[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    int n = 0;
+    for (int i = 0; i < 32; ++i) { t += sv[i]; n += sc[i]; }
+    *loss = n > 0 ? (float)(t / n) : __int_as_float(0x7fc00000);     // no counted label: nan, like torch
+  }
+}
+
 // Generic dtype conversion to bf16 / fp32 staging (weights upload).
 template <typename T>
 __global__ void convert_to_bf16_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {

@@ -457,9 +457,13 @@ class ValleyLlamaForCausalLM:
             logits, nxt = self._prefill(cache, inputs_embeds, 2 if self.logits_all_positions else 1)
         loss = None
         if labels is not None:       # valley_model.py:308-318
-            sl = logits[..., :-1, :].reshape(-1, self.config.vocab_size)
-            tl = labels.to(self.device)[..., 1:].reshape(-1)
-            loss = torch.nn.functional.cross_entropy(sl, tl, ignore_index=IGNORE_INDEX)
+            if logits.shape[1] != S:
+                raise ValueError("labels need logits at every position (logits_all_positions=True, the reference behaviour)")
+            lab = labels.to(self.device, torch.int64).contiguous()
+            loss = torch.full((), float("nan"), dtype=torch.float32, device=self.device)     # S == 1: nothing to score (torch: nan)
+            if S >= 2:
+                check(self._lib.vly_cross_entropy(self._ctx, logits.data_ptr(), lab.data_ptr(), B, S, IGNORE_INDEX,
+                                                  loss.data_ptr(), _stream()))
         out = CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=cache)
         out.next_tokens = nxt
         if return_dict is False:
