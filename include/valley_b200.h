@@ -182,6 +182,7 @@ typedef struct {
   uint64_t seed;
   int64_t eos_token_id;      /* -1: none */
   int64_t pad_token_id;
+  int64_t stop_token_id;     /* -1: none; a second id that ends a row: the worker's single-token stop string (model_worker.py:355-360, :396-397) */
 } vly_sampling;
 
 /* the first generated token: select from the prefill's last-position logits [B,V] fp32 (vly_llama_prefill logits_mode 1);

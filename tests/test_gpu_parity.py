@@ -526,6 +526,99 @@ def test_forward_with_labels_returns_the_reference_loss():
     assert torch.isnan(allign.loss)                                  # nothing counted: nan, like nn.CrossEntropyLoss
 
 
+class _FakeTokenizer:
+    """Word-level tokenizer over the model's id space: special strings -> the sentinel ids, 'w<id>' words -> id."""
+    eos_token_id = 2
+
+    def __init__(self, spec, add_bos=True):
+        import re
+        self.add_bos = add_bos
+        t = syn.sentinel_ids(spec)
+        self.special = {"<im_patch>": t["im_patch_token"], "<im_start>": t["im_start_token"], "<im_end>": t["im_end_token"],
+                        "<vi_frame>": t["vi_frame_token"], "<vi_start>": t["vi_start_token"], "<vi_end>": t["vi_end_token"]}
+        self.rx = re.compile(r"<[a-z_]+>|w\d+")
+
+    def __call__(self, text):
+        import types
+        ids = ([1] if self.add_bos else []) + [self.special[m] if m in self.special else int(m[1:]) for m in self.rx.findall(text)]
+        return types.SimpleNamespace(input_ids=ids)
+
+    def decode(self, ids, skip_special_tokens=True):
+        return "".join(f" w{int(i)}" for i in ids if int(i) not in (1, 2))
+
+
+def _reference_worker_loop(m, tokenizer, params, stream_interval, context_len=2048):
+    """model_worker.py:319-426 verbatim in structure (one forward per token, host sync per token), over OUR model."""
+    from valley_b200 import serving
+    prompt = params["prompt"]
+    ori_prompt, video = prompt, params.get("video")
+    prompt = serving.expand_video_prompt(prompt, video.shape[0], True)
+    temperature, max_new_tokens = float(params.get("temperature", 1.0)), min(int(params.get("max_new_tokens", 256)), 1024)
+    stop_str = params.get("stop")
+    stop_idx = serving.stop_token_index(tokenizer, stop_str)
+    input_ids = tokenizer(prompt).input_ids
+    input_ids = input_ids[-(context_len - max_new_tokens - 8):]
+    pred_ids, past, outs = [], None, []
+    for i in range(max_new_tokens):
+        if i == 0:
+            out = m(torch.as_tensor([input_ids]).cuda(), use_cache=True, images=video.cuda().half().unsqueeze(0))
+        else:
+            out = m(input_ids=torch.as_tensor([[token]], device="cuda"), use_cache=True, past_key_values=past,
+                    attention_mask=torch.ones(1, past[0][0].shape[-2] + 1, device="cuda"))
+        past = out.past_key_values
+        assert temperature < 1e-4
+        token = int(torch.argmax(out.logits[0][-1]))
+        pred_ids.append(token)
+        stopped = (stop_idx is not None and token == stop_idx) or token == tokenizer.eos_token_id
+        if i % stream_interval == 0 or i == max_new_tokens - 1 or stopped:
+            cur_out = tokenizer.decode(pred_ids, skip_special_tokens=True)
+            pos = cur_out.rfind(stop_str) if stop_str is not None else -1
+            if pos != -1:
+                cur_out, stopped = cur_out[:pos], True
+            outs.append(ori_prompt + cur_out)
+        if stopped:
+            break
+    return outs, pred_ids
+
+
+@pytest.mark.parametrize("interval", [1, 2, 5])
+def test_generate_stream_matches_the_reference_worker_loop(interval):
+    """valley_b200.serving.generate_stream (device loop in chunks of stream_interval) yields the same texts at the same
+    points as the reference worker's token-by-token loop: plain run, single-token stop id, multi-token stop string, eos."""
+    from valley_b200 import serving
+    spec, sd, m = get("tiny")
+    tk = _FakeTokenizer(spec)
+    video = syn.make_pixels(1, 3, 8)[0]
+    words = " ".join(f"w{i}" for i in torch.randint(3, 900, (12,), generator=torch.Generator().manual_seed(1)).tolist())
+    base = dict(prompt=f"{words} <video> w77 w78", video=video, temperature=0.0, max_new_tokens=11)
+    ref_outs, ref_ids = _reference_worker_loop(m, tk, base, interval)
+    got = [d["text"] for d in serving.generate_stream(m, tk, base, stream_interval=interval)]
+    assert got == ref_outs and len(ref_ids) == 11
+    assert all(d["error_code"] == 0 for d in serving.generate_stream(m, tk, base, stream_interval=interval))
+    # single-token stop string -> stop id handled on the device (model_worker.py:354-360, :396-397)
+    # (with a BOS-prepending tokenizer the stop string is never ONE id -- a quirk of the reference -- so: a tokenizer without BOS)
+    tk1 = _FakeTokenizer(spec, add_bos=False)
+    r1_plain, ids1 = _reference_worker_loop(m, tk1, base, interval)
+    p1 = dict(base, stop=f" w{ids1[4]}")
+    assert serving.stop_token_index(tk1, p1["stop"]) == ids1[4] and serving.stop_token_index(tk, p1["stop"]) is None
+    r1, rid1 = _reference_worker_loop(m, tk1, p1, interval)
+    g1 = [d["text"] for d in serving.generate_stream(m, tk1, p1, stream_interval=interval)]
+    assert g1 == r1 and len(rid1) <= 5 and not r1[-1].endswith(p1["stop"])
+    # multi-token stop string: only found at emission points (the text check), cut off the output
+    p2 = dict(base, stop=f" w{ref_ids[5]} w{ref_ids[6]}")
+    r2, _ = _reference_worker_loop(m, tk, p2, interval)
+    g2 = [d["text"] for d in serving.generate_stream(m, tk, p2, stream_interval=interval)]
+    assert g2 == r2 and p2["stop"] not in r2[-1]
+    # eos
+    tk3 = _FakeTokenizer(spec)
+    tk3.eos_token_id = ref_ids[3]
+    r3, ids3 = _reference_worker_loop(m, tk3, base, interval)
+    g3 = [d["text"] for d in serving.generate_stream(m, tk3, base, stream_interval=interval)]
+    assert g3 == r3 and len(ids3) == 4
+    with pytest.raises(AssertionError):
+        list(serving.generate_stream(m, tk, dict(base, prompt="w5 w6"), stream_interval=interval))
+
+
 def test_cache_capacity_is_enforced():
     spec, sd, m = get("tiny")
     ids = syn.make_prompt_ids(spec, 1, 2, 0)

@@ -33,7 +33,11 @@ class VlyTokens(C.Structure):
 
 
 class VlySampling(C.Structure):
-    _fields_ = [("temperature", C.c_float), ("seed", C.c_uint64), ("eos_token_id", C.c_int64), ("pad_token_id", C.c_int64)]
+    _fields_ = [("temperature", C.c_float), ("seed", C.c_uint64), ("eos_token_id", C.c_int64), ("pad_token_id", C.c_int64),
+                ("stop_token_id", C.c_int64)]
+
+    def __init__(self, temperature=0.0, seed=0, eos_token_id=-1, pad_token_id=0, stop_token_id=-1):
+        super().__init__(temperature, seed, eos_token_id, pad_token_id, stop_token_id)
 
 
 VLY_OK, VLY_ERR_INVALID, VLY_ERR_CUDA, VLY_ERR_STATE = 0, -1, -2, -3

@@ -1143,7 +1143,7 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   CK(cudaMalloc((void**)&kv->d_sample, sizeof(SampleState)));
   {
     SampleState s0 = {};
-    s0.inv_temp = 1.f; s0.eos = -1; s0.pad = 0;
+    s0.inv_temp = 1.f; s0.eos = -1; s0.pad = 0; s0.stop2 = -1;
     CK(cudaMemcpy(kv->d_sample, &s0, sizeof(s0), cudaMemcpyHostToDevice));
   }
   CK(cudaMalloc((void**)&kv->key_bits, (size_t)batch * kv->mask_words() * 4));
@@ -1616,9 +1616,9 @@ static int enqueue_full_step(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
 
 // ---- token selection state ----
 __global__ void set_sample_state_kernel(SampleState* s, float inv_temp, int enabled, uint32_t k0, uint32_t k1, long long eos, long long pad,
-                                        int reset_done) {
+                                        long long stop2, int reset_done) {
   if (threadIdx.x == 0) {
-    s->inv_temp = inv_temp; s->enabled = enabled; s->seed_lo = k0; s->seed_hi = k1; s->eos = eos; s->pad = pad;
+    s->inv_temp = inv_temp; s->enabled = enabled; s->seed_lo = k0; s->seed_hi = k1; s->eos = eos; s->pad = pad; s->stop2 = stop2;
     if (reset_done) { s->all_done = 0; s->steps_valid = 0; }
   }
   if (reset_done && threadIdx.x < kMaxSampleRows) s->done[threadIdx.x] = 0;
@@ -1628,14 +1628,14 @@ __global__ void set_sample_state_kernel(SampleState* s, float inv_temp, int enab
 static int set_sampling(vly_ctx* c, vly_kv* kv, const vly_sampling* sp, bool reset_done, cudaStream_t st) {
   if (!sp) {
     if (!kv->sample_dirty) return VLY_OK;
-    set_sample_state_kernel<<<1, 64, 0, st>>>(kv->d_sample, 1.f, 0, 0, 0, -1, 0, 1);
+    set_sample_state_kernel<<<1, 64, 0, st>>>(kv->d_sample, 1.f, 0, 0, 0, -1, 0, -1, 1);
     kv->sample_dirty = false;
   } else {
     if (kv->B > kMaxSampleRows) return fail(VLY_ERR_INVALID, "sampling / eos bookkeeping supports at most %d sequences per cache", kMaxSampleRows);
     const bool on = sp->temperature >= 1e-4f;         // model_worker.py:390: below that the reference takes the arg-max
     set_sample_state_kernel<<<1, 64, 0, st>>>(kv->d_sample, on ? 1.f / sp->temperature : 1.f, on ? 1 : 0, (uint32_t)sp->seed,
                                               (uint32_t)(sp->seed >> 32), sp->eos_token_id < 0 ? -1 : sp->eos_token_id, sp->pad_token_id,
-                                              reset_done ? 1 : 0);
+                                              sp->stop_token_id < 0 ? -1 : sp->stop_token_id, reset_done ? 1 : 0);
     kv->sample_dirty = true;
   }
   c->launches++;
@@ -1713,7 +1713,7 @@ static int generate_impl(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, in
   if (steps_done_dev)      // (zeroed below, before the first step)
     CK(cudaMemcpyAsync(steps_done_dev, &kv->d_sample->steps_valid, 4, cudaMemcpyDeviceToDevice, st));
   kv->host_len += n_steps;
-  if (sp && sp->eos_token_id >= 0) kv->len_dirty = true;      // the loop may have stopped early: the device holds the true length
+  if (sp && (sp->eos_token_id >= 0 || sp->stop_token_id >= 0)) kv->len_dirty = true;      // the loop may have stopped early: the device holds the true length
   return VLY_OK;
 }
 

@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
       *p.step += 1;
       *p.seq_len += 1;
       p.sample->steps_valid += 1;
-      if (p.sample->eos >= 0) {
+      if (p.sample->eos >= 0 || p.sample->stop2 >= 0) {
         int all = 1;
         for (int b = 0; b < p.B; ++b) all &= p.sample->done[b];
         p.sample->all_done = all;

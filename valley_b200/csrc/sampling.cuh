@@ -26,6 +26,7 @@ struct SampleState {          // lives in device memory next to the KV cache; re
   int enabled;                // 0 = greedy (scores are the raw logits: bit-identical to the plain arg-max)
   uint32_t seed_lo, seed_hi;
   long long eos, pad;         // eos < 0: no stop token
+  long long stop2;            // second stop id (the worker's single-token stop string, model_worker.py:355-360); < 0: none
   int all_done;               // every row has produced eos: further steps exit at once
   int steps_valid;            // decode steps executed before all_done was raised (the one that raised it included)
   int done[kMaxSampleRows];
@@ -53,9 +54,9 @@ __device__ __forceinline__ float sample_score(float logit, float inv_temp, uint3
 
 // eos / pad bookkeeping for one row's freshly selected token; returns the token to emit
 __device__ __forceinline__ long long sample_finish_row(SampleState* s, int b, long long tok) {
-  if (s->eos < 0) return tok;
+  if (s->eos < 0 && s->stop2 < 0) return tok;
   if (s->done[b]) return s->pad;
-  if (tok == s->eos) s->done[b] = 1;
+  if (tok == s->eos || tok == s->stop2) s->done[b] = 1;     // (ids are >= 0, an unset -1 never matches)
   return tok;
 }
 
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(1024) sample_rows_kernel(const float* __restri
     if (tid == 0) { s->all_done = 0; s->steps_valid = 0; }
     __syncthreads();
   } else {
-    if (!s->enabled && s->eos < 0) return;          // plain greedy: the arg-max epilogue already wrote the token
+    if (!s->enabled && s->eos < 0 && s->stop2 < 0) return;   // plain greedy: the arg-max epilogue already wrote the token
     if (s->all_done) {                              // every row finished earlier: keep emitting pad
       if (tid < B) {
         next_tokens[tid] = s->pad;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(1024) sample_rows_kernel(const float* __restri
   }
   if (tid == 0) {
     if (!reset) s->steps_valid += 1;
-    if (s->eos >= 0) {
+    if (s->eos >= 0 || s->stop2 >= 0) {
       int all = 1;
       for (int b = 0; b < B; ++b) all &= s->done[b];
       s->all_done = all;
