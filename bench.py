@@ -282,6 +282,17 @@ def main():
             ms = t.item()
         return ms / K, model.launches() - l0, r
 
+    if os.environ.get("VLY_BENCH_PROFILE"):
+        # ncu launch list of exactly the timed step:  ncu --profile-from-start off --metrics gpu__time_duration.sum ... bench.py
+        for _ in range(max(a.warmup, 3)):
+            step_device()
+        barrier()
+        torch.cuda.profiler.start()
+        step_device()
+        barrier()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled": "one timed step", "launches": int(model.launches())}))
+        return
     clk = ClockSampler(local)
     if rank == 0:
         clk.start()
@@ -386,7 +397,7 @@ def main():
         "vit_frames_per_s": world * fps8, "vit_ms_8_frames": ms_vit8, "prefill_ms": ms_prefill, "vit_sweep_frames_per_s": sweep,
         "roofline": {"kernel": "decode_step_kernel (one persistent cooperative launch = one decode step: all weights streamed once through a TMA ring)",
                      "bound": "hbm", "achieved": dec_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": dec_gbs / pk["hbm"], "peak_source": pk["src"],
-                     "algorithmic_bytes_per_launch": dec_bytes, "traffic": ncu_traffic("prof_mega_r01_summary.csv"),
+                     "algorithmic_bytes_per_launch": dec_bytes, "traffic": ncu_traffic("prof_mega_r01_final_summary.csv"),
                      "note": "peak = measured read+write copy bandwidth; a read-only stream on this part reaches 7.2-7.5 TB/s (tools/membw.cu)"},
         "roofline_vit": None if gf is None else {
             "kernel": "ViT-L/14 encode (gemm_tc_kernel + vit_attention_kernel), F=8", "bound": "tensor",

@@ -167,7 +167,8 @@ struct vly_kv {
   uint32_t* key_bits = nullptr;       // [B, Smax/32] attention_mask bits (1 = attend); all ones unless vly_kv_set_key_mask
   bool masked = false;
   int mask_words() const { return Smax / 32; }
-  cudaGraphExec_t graph = nullptr;
+  cudaGraphExec_t graph = nullptr;     // one decode step
+  cudaGraphExec_t graph_n = nullptr;   // kGraphSteps steps in one graph (fewer graph launches, kernel->kernel edges inside)
   int graph_nodes = 0;
   size_t layer_stride() const { return (size_t)2 * B * ctx->cfg.num_attention_heads * Smax * 128; }
   bf16* k_layer(int l) const { return cache + (size_t)l * layer_stride(); }
@@ -1131,9 +1132,9 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   CK(cudaMalloc((void**)&kv->hb, (size_t)batch * I * 2));
   CK(cudaMalloc((void**)&kv->part_o, (size_t)batch * nH * kv->nsplit * 128 * 4));
   CK(cudaMalloc((void**)&kv->part_ml, (size_t)batch * nH * kv->nsplit * sizeof(float2)));
-  CK(cudaMalloc((void**)&kv->counters, ((size_t)batch * nH + 2) * 4));
-  CK(cudaMemset(kv->counters, 0, ((size_t)batch * nH + 2) * 4));
-  kv->grid_counter = kv->counters + (size_t)batch * nH + 1;
+  CK(cudaMalloc((void**)&kv->counters, ((size_t)batch * nH + 4) * 4));
+  CK(cudaMemset(kv->counters, 0, ((size_t)batch * nH + 4) * 4));
+  kv->grid_counter = kv->counters + (size_t)batch * nH + 1;      // [+2] = launch epoch of the grid barrier
   CK(cudaMalloc((void**)&kv->part_val, (size_t)batch * kv->gemv_grid * 4));
   CK(cudaMalloc((void**)&kv->part_idx, (size_t)batch * kv->gemv_grid * 4));
   CK(cudaMalloc((void**)&kv->logits, (size_t)batch * V * 4));
@@ -1174,6 +1175,7 @@ extern "C" void vly_kv_destroy(vly_kv* kv) {
   if (!kv) return;
   cudaSetDevice(kv->ctx->cfg.device);
   if (kv->graph) cudaGraphExecDestroy(kv->graph);
+  if (kv->graph_n) cudaGraphExecDestroy(kv->graph_n);
   void* ps[] = {kv->d_sample, kv->key_bits, kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
   for (void* p : ps)
     if (p) cudaFree(p);
@@ -1548,6 +1550,7 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   p.logits = kv->logits; p.part_val = kv->part_val; p.part_idx = kv->part_idx;
   p.next_tokens = kv->cur_tokens; p.out_tokens = kv->gen_tokens; p.out_stride = kv->Smax;
   p.grid_counter = kv->grid_counter;
+  p.grid_epoch = kv->grid_counter + 1;
   p.sample = kv->d_sample;
   {
     static const bool want = getenv("VLY_MEGA_DBG") != nullptr;
@@ -1577,7 +1580,6 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   if (n_stages < 2) return fail(VLY_ERR_INVALID, "decode: activations (B=%d, K=%d) leave no room for the weight ring", B, p.Kmax);
   p.n_stages = n_stages;
   const size_t smem = (size_t)n_stages * stage_b + x_bytes + misc;
-  CK(cudaMemsetAsync(kv->grid_counter, 0, 4, st));
   void* args[] = {&p};
   cudaError_t e;
 #define VLY_MEGA_CASE(BM)                                                                                               \
@@ -1643,23 +1645,31 @@ static int set_sampling(vly_ctx* c, vly_kv* kv, const vly_sampling* sp, bool res
   return VLY_OK;
 }
 
-static int build_graph(vly_ctx* c, vly_kv* kv) {
-  if (kv->graph) return VLY_OK;
+constexpr int kGraphSteps = 8;
+static int capture_steps(vly_ctx* c, vly_kv* kv, int n, cudaGraphExec_t* out) {
   const int64_t before = c->launches;
   CK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
-  const int r = enqueue_full_step(c, kv, c->cap_stream);
+  int r = VLY_OK;
+  for (int i = 0; i < n && r == VLY_OK; ++i) r = enqueue_full_step(c, kv, c->cap_stream);
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
-  kv->graph_nodes = (int)(c->launches - before);
+  kv->graph_nodes = (int)((c->launches - before) / n);
   c->launches = before;
   if (r != VLY_OK) {
     if (graph) cudaGraphDestroy(graph);
     return r;
   }
   if (e != cudaSuccess) return fail(VLY_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-  const cudaError_t e2 = cudaGraphInstantiate(&kv->graph, graph, 0);
+  const cudaError_t e2 = cudaGraphInstantiate(out, graph, 0);
   cudaGraphDestroy(graph);
   if (e2 != cudaSuccess) return fail(VLY_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2));
+  return VLY_OK;
+}
+static int build_graph(vly_ctx* c, vly_kv* kv) {
+  if (kv->graph) return VLY_OK;
+  TRY(capture_steps(c, kv, 1, &kv->graph));
+  static const bool multi = getenv("VLY_GRAPH_STEPS1") == nullptr;
+  if (multi) TRY(capture_steps(c, kv, kGraphSteps, &kv->graph_n));
   return VLY_OK;
 }
 
@@ -1702,9 +1712,10 @@ static int generate_impl(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, in
   CK(cudaMemcpyAsync(kv->cur_tokens, first_tokens, (size_t)kv->B * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(kv->d_step, 0, 4, st));
   if (steps_done_dev) CK(cudaMemsetAsync(&kv->d_sample->steps_valid, 0, 4, st));
-  for (int i = 0; i < n_steps; ++i) {
-    if (no_graph) TRY(enqueue_full_step(c, kv, st));
-    else CK(cudaGraphLaunch(kv->graph, st));
+  for (int i = 0; i < n_steps;) {
+    if (no_graph) { TRY(enqueue_full_step(c, kv, st)); ++i; }
+    else if (kv->graph_n && n_steps - i >= kGraphSteps) { CK(cudaGraphLaunch(kv->graph_n, st)); i += kGraphSteps; }
+    else { CK(cudaGraphLaunch(kv->graph, st)); ++i; }
   }
   if (!no_graph) c->launches += (int64_t)n_steps * kv->graph_nodes;
   if (out_tokens)

@@ -61,7 +61,8 @@ struct StepParams {
   long long* out_tokens;        // [B, out_stride]
   int out_stride;
   SampleState* sample;          // token selection state (greedy / temperature sampling, eos bookkeeping); sampling.cuh
-  unsigned int* grid_counter;   // zeroed by the host before every launch
+  unsigned int* grid_counter;   // monotonically increasing arrival counter of the grid barrier (never reset: no memset node per step)
+  unsigned int* grid_epoch;     // launches that ran to completion; barrier k of a launch waits for (epoch * n_barriers + k) * gridDim
   int n_stages;
   int n_inflight;               // bulk copies outstanding per SM are capped at this many stages (the ring may be deeper)
   long long* dbg;               // optional [gridDim][8] cycle counters: sync, stage-x, weight loop, attention, full-wait
@@ -109,7 +110,7 @@ VLY_DEVINL void grid_sync_consumers(unsigned int* counter, unsigned int target, 
   asm volatile("bar.sync 2, 544;" ::: "memory");          // every write of this CTA happens-before thread 0's release
   if (ct == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
-    while (ld_acquire_u32(counter) < target) {
+    while ((int)(ld_acquire_u32(counter) - target) < 0) {     // wrap-safe
     }
   }
   asm volatile("bar.sync 2, 544;" ::: "memory");
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
   const float samp_it = p.sample->inv_temp;
   const uint32_t samp_k0 = p.sample->seed_lo, samp_k1 = p.sample->seed_hi;
   unsigned int sync_no = 0;
+  // written by block 0 at the very end of the previous completed launch (stream order): the same value in every CTA
+  const unsigned int sync_base = *p.grid_epoch * (unsigned int)(p.n_phases + 1) * gridDim.x;
   long long t_sync = 0, t_stage = 0, t_loop = 0, t_attn = 0, t0 = clock64();
   // ---- phase -1: x = embed[token] (decode input) ----
   {
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
       bestv[lane] = -INFINITY;
       besti[lane] = 0;
     }
-    grid_sync_consumers(p.grid_counter, (++sync_no) * gridDim.x, ct);
+    grid_sync_consumers(p.grid_counter, sync_base + (++sync_no) * gridDim.x, ct);
     t_sync += clock64() - t0;
   }
 
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
       p.part_val[(size_t)lane * gridDim.x + blockIdx.x] = bestv[lane];
       p.part_idx[(size_t)lane * gridDim.x + blockIdx.x] = besti[lane];
     }
-    grid_sync_consumers(p.grid_counter, (++sync_no) * gridDim.x, ct);
+    grid_sync_consumers(p.grid_counter, sync_base + (++sync_no) * gridDim.x, ct);
     t_sync += clock64() - t0;
   }
   if (p.dbg != nullptr && ct == 0) {
@@ -596,6 +599,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
     if (ct == 0) {
       *p.step += 1;
       *p.seq_len += 1;
+      *p.grid_epoch += 1;          // every CTA has passed the last barrier of this launch (they read the epoch at their start)
       p.sample->steps_valid += 1;
       if (p.sample->eos >= 0 || p.sample->stop2 >= 0) {
         int all = 1;
