@@ -429,7 +429,9 @@ extern "C" void vly_destroy(vly_ctx* c) {
   cudaSetDevice(c->cfg.device);
   for (auto& kvp : c->staged) cudaFree(kvp.second.dev);
   for (void* p : c->owned) cudaFree(p);
-  Buf* bufs[] = {&c->w_col, &c->w_patch, &c->w_qkv, &c->w_ctx, &c->w_h, &c->w_stats, &c->w_pool, &c->w_x, &c->w_q, &c->w_attn, &c->w_hb, &c->w_pstats};
+  Buf* bufs[] = {&c->w_col, &c->w_patch, &c->w_qkv, &c->w_ctx, &c->w_h, &c->w_stats, &c->w_pool, &c->w_x, &c->w_q, &c->w_attn, &c->w_hb, &c->w_pstats,
+                 &c->w_xlocal, &c->w_score, &c->w_pall, &c->w_xp, &c->w_dkv, &c->w_dq, &c->w_datt, &c->w_dx1, &c->w_df1, &c->w_dx2, &c->w_strip,
+                 &c->w_tables};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
