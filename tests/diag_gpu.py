@@ -1,5 +1,5 @@
-"""Stage-by-stage GPU diagnostics (prints metrics, never hides a failure).  Run each stage under `timeout`:
-    timeout 180 python tools/gpu_diag.py gemm | vitattn | vit | splice | prefill | decode | e2e
+"""Stage-by-stage GPU diagnostics against the oracle (test infrastructure; prints metrics, never hides a failure).  Run each stage under `timeout`:
+    timeout 180 python tests/diag_gpu.py gemm | vitattn | vit | splice | prefill | decode | e2e
 """
 import ctypes as C
 import os
