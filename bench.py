@@ -45,6 +45,22 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def usable_cpus():
+    """cpus this process may actually use: affinity mask and cgroup quota, not the machine's core count"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def ncu_traffic(name):
     """dram__bytes_read.sum + dram__bytes_write.sum of the kernel's committed ncu --set full capture (profiles/), per launch."""
     try:
@@ -120,8 +136,9 @@ def cpu_reference_arm(spec, n_new=N_NEW, n_frames=N_FRAMES, sample_layers=2, dec
     without AMX / AVX512-BF16)."""
     import dataclasses
     from oracle import valley_oracle as O
-    torch.set_num_threads(os.cpu_count())
-    cores = torch.get_num_threads()
+    usable = usable_cpus()
+    cands = sorted({n for n in (usable, usable // 2, usable // 4, usable // 8, 64, 32, 16, 8) if 1 <= n <= usable}, reverse=True)
+    torch.set_num_threads(usable)
     L = spec.num_hidden_layers
     t0 = time.time()
     name = {torch.bfloat16: "bf16", torch.float32: "fp32"}
@@ -160,18 +177,33 @@ def cpu_reference_arm(spec, n_new=N_NEW, n_frames=N_FRAMES, sample_layers=2, dec
             t_head_dec = time.time() - t
         return t_pre, t_head, t_layers, t_head_dec
 
+    def best_threads(fn):
+        """the thread count that is fastest on this box for this phase (a container's CPU quota is often far below
+        os.cpu_count(); oversubscribing the ATen pool then costs orders of magnitude)"""
+        best = None
+        for n in cands:
+            torch.set_num_threads(n)
+            t = fn()
+            if best is None or t < best[0]:
+                best = (t, n)
+        torch.set_num_threads(best[1])
+        return best[1]
+
     vit_time(torch.float32, 1)                                               # first-touch warm-up
+    th_vit = best_threads(lambda: vit_time(torch.float32, 1))
     dt_vit = min((torch.bfloat16, torch.float32), key=lambda d: vit_time(d, 2))
-    dt_llm = min((torch.bfloat16, torch.float32), key=lambda d: sum(llm_times(d, 1)[2:]))
     t_vit = vit_time(dt_vit, n_frames)
+    th_llm = best_threads(lambda: sum(llm_times(torch.float32, 1)[2:]))
+    dt_llm = min((torch.bfloat16, torch.float32), key=lambda d: sum(llm_times(d, 1)[2:]))
     t_pre, t_head, t_layers, t_head_dec = llm_times(dt_llm, decode_tokens)
+    cores = th_llm
     t_prefill = t_pre * L / sample_layers + t_head
     t_step_dec = t_layers * L / sample_layers + t_head_dec
     total = t_vit + t_prefill + n_new * t_step_dec
     return dict(tokens_per_s=n_new / total, vit_frames_per_s=n_frames / t_vit, decode_tokens_per_s=1.0 / t_step_dec,
                 prefill_s=t_prefill, cores=cores, wall_s=time.time() - t0,
-                sample=f"CPU, {cores} threads, ViT in {name[dt_vit]} / LLaMA in {name[dt_llm]} (faster of bf16/fp32 per phase, probed on the "
-                       f"workload): full ViT-L/14 ({spec.vit_layers + 1 + spec.mm_vision_select_layer} layers) on {n_frames} frames; "
+                sample=f"CPU, {usable} usable cpus; ViT on {th_vit} threads in {name[dt_vit]}, LLaMA on {th_llm} threads in {name[dt_llm]} (thread "
+                       f"count and bf16/fp32 chosen per phase by timing the workload): full ViT-L/14 ({spec.vit_layers + 1 + spec.mm_vision_select_layer} layers) on {n_frames} frames; "
                        f"LLaMA {sample_layers}/{L} layers + lm_head, prefill S={S} once and {decode_tokens} decode tokens, layer time scaled x{L // sample_layers}")
 
 

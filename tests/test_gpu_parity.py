@@ -619,6 +619,21 @@ def test_generate_stream_matches_the_reference_worker_loop(interval):
         list(serving.generate_stream(m, tk, dict(base, prompt="w5 w6"), stream_interval=interval))
 
 
+def test_from_pretrained_checkpoint_directory(tmp_path):
+    """ValleyLlamaForCausalLM.from_pretrained(dir) (run_valley.py:39): same logits as loading the same tensors by hand."""
+    from test_host_logic import _write_checkpoint
+    from valley_b200.model import ValleyLlamaForCausalLM
+    spec, sd, m = get("tiny")
+    _write_checkpoint(str(tmp_path), spec, {k: v.bfloat16() for k, v in sd.items()}, "safetensors")
+    m2 = ValleyLlamaForCausalLM.from_pretrained(str(tmp_path), torch_dtype=torch.float16)
+    for k, v in syn.sentinel_ids(spec).items():
+        setattr(m2.get_model().vision_tower.config, k, v)
+    ids, px = syn.make_prompt_ids(spec, 1, 2, 0), syn.make_pixels(1, 2, 0)
+    a = m(input_ids=ids.cuda(), images=px.cuda()).logits
+    b = m2(input_ids=ids.cuda(), images=px.cuda()).logits
+    assert torch.equal(a, b)
+
+
 def test_cache_capacity_is_enforced():
     spec, sd, m = get("tiny")
     ids = syn.make_prompt_ids(spec, 1, 2, 0)

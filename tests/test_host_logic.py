@@ -155,3 +155,52 @@ def test_frame_index_selection_matches_oracle():
         assert np.array_equal(video.fps_frame_indices(n, fps), P.fps_frame_indices(n, fps))
     with pytest.raises(ValueError):
         video.preprocess_plan(0, 10)
+
+
+def _write_checkpoint(tmp, spec, sd, fmt):
+    """HF save_pretrained layout: config.json (+ a local CLIP config dir) and two weight shards with an index."""
+    import json
+    import os
+    vt = os.path.join(tmp, "clip")
+    os.makedirs(vt, exist_ok=True)
+    json.dump(dict(hidden_size=spec.vit_hidden, intermediate_size=spec.vit_mlp, num_hidden_layers=spec.vit_layers,
+                   num_attention_heads=spec.vit_heads, image_size=spec.vit_image, patch_size=spec.vit_patch, layer_norm_eps=spec.vit_eps),
+              open(os.path.join(vt, "config.json"), "w"))
+    json.dump(dict(architectures=["ValleyLlamaForCausalLM"], model_type="valley", hidden_size=spec.hidden_size,
+                   num_hidden_layers=spec.num_hidden_layers, num_attention_heads=spec.num_attention_heads,
+                   intermediate_size=spec.intermediate_size, vocab_size=spec.vocab_size, rms_norm_eps=spec.rms_norm_eps,
+                   max_position_embeddings=spec.max_position_embeddings, mm_vision_tower=vt, mm_vision_select_layer=spec.mm_vision_select_layer,
+                   use_mm_proj=True, mm_hidden_size=spec.vit_hidden, mm_use_im_start_end=True, torch_dtype="float16"),
+              open(os.path.join(tmp, "config.json"), "w"))
+    names = list(sd)
+    halves = [names[: len(names) // 2], names[len(names) // 2:]]
+    wm = {}
+    for i, part in enumerate(halves):
+        if fmt == "safetensors":
+            from safetensors.torch import save_file
+            fn = f"model-{i + 1:05d}-of-00002.safetensors"
+            save_file({k: sd[k].contiguous() for k in part}, os.path.join(tmp, fn))
+        else:
+            fn = f"pytorch_model-{i + 1:05d}-of-00002.bin"
+            torch.save({k: sd[k] for k in part}, os.path.join(tmp, fn))
+        wm.update({k: fn for k in part})
+    idx = "model.safetensors.index.json" if fmt == "safetensors" else "pytorch_model.bin.index.json"
+    json.dump(dict(metadata={}, weight_map=wm), open(os.path.join(tmp, idx), "w"))
+
+
+@pytest.mark.parametrize("fmt", ["safetensors", "bin"])
+def test_checkpoint_directory_reader(tmp_path, fmt):
+    """from_pretrained's host side: config.json (+ CLIP geometry from a local tower dir) and sharded weights, streamed by name."""
+    from valley_b200 import checkpoint
+    from valley_b200.model import ValleyConfig
+    spec = syn.TINY
+    sd = {k: v.half() for k, v in syn.make_state_dict(spec, 0).items()}
+    _write_checkpoint(str(tmp_path), spec, sd, fmt)
+    cfg = ValleyConfig(**checkpoint.read_config(str(tmp_path)))
+    assert (cfg.hidden_size, cfg.num_hidden_layers, cfg.vit_layers, cfg.vit_heads, cfg.vocab_size) == (512, 2, 3, 16, 1032)
+    assert cfg.patch_pooling_method == "mean" and cfg.mm_vision_select_layer == -2
+    got = dict(checkpoint.iter_checkpoint(str(tmp_path)))
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    assert len(checkpoint.weight_files(str(tmp_path))) == 2
+    with pytest.raises(FileNotFoundError):
+        checkpoint.weight_files(str(tmp_path / "clip"))

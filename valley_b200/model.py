@@ -237,6 +237,17 @@ class ValleyLlamaForCausalLM:
             pass
 
     @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype=None, device=0, **kw) -> "ValleyLlamaForCausalLM":
+        """``ValleyLlamaForCausalLM.from_pretrained(path, torch_dtype=torch.float16)`` (run_valley.py:39, model_worker.py:62): a
+        local HF checkpoint directory (config.json + safetensors / .bin shards).  Weights are stored as bf16 whatever ``torch_dtype``
+        says (fp16 checkpoints are converted on load)."""
+        from . import checkpoint
+        cfg = ValleyConfig(**{**checkpoint.read_config(pretrained_model_name_or_path), **kw})
+        m = cls(cfg, device)
+        m.load_state_dict(checkpoint.iter_checkpoint(pretrained_model_name_or_path))
+        return m
+
+    @classmethod
     def from_state_dict(cls, config: ValleyConfig, state: Iterable, device=0) -> "ValleyLlamaForCausalLM":
         m = cls(config, device)
         m.load_state_dict(state)
