@@ -1218,6 +1218,7 @@ __global__ void pack_key_mask_kernel(const uint8_t* __restrict__ mask, int len, 
 
 extern "C" int vly_kv_set_key_mask(vly_kv* kv, const uint8_t* mask_dev, int len, void* stream) {
   if (!kv || len < 0 || len > kv->Smax || (len > 0 && !mask_dev)) return fail(VLY_ERR_INVALID, "vly_kv_set_key_mask: bad argument (len %d, capacity %d)", len, kv ? kv->Smax : 0);
+  std::lock_guard<std::mutex> lk(kv->ctx->mu);
   CK(cudaSetDevice(kv->ctx->cfg.device));
   const int words = kv->mask_words();
   if (len == 0) {
