@@ -207,6 +207,59 @@ def cpu_reference_arm(spec, n_new=N_NEW, n_frames=N_FRAMES, sample_layers=2, dec
                        f"LLaMA {sample_layers}/{L} layers + lm_head, prefill S={S} once and {decode_tokens} decode tokens, layer time scaled x{L // sample_layers}")
 
 
+def gpu_eager_reference(spec, n_frames=N_FRAMES, decode_tokens=16):
+    """SURVEY 8d "reference GPU path": the same oracle (the ATen ops the reference's HF modules run, eager, bf16) on the B200 itself.
+    Not a target and not the product -- it says how much of the speed-up is the GPU and how much is this repo."""
+    from oracle import valley_oracle as O
+    dev, dt = "cuda", torch.bfloat16
+    w = dict(syn.iter_state_dict(spec, 0, device=dev, dtype=dt))
+    S = 1 + 40 + 1 + 256 + 2 + n_frames + 1 + 24
+    px = syn.make_pixels(1, n_frames, 0)[0].to(dev, dt)
+    kw = dict(n_layers=spec.num_hidden_layers, heads=spec.num_attention_heads, eps=spec.rms_norm_eps)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for _ in range(2):
+            O.vit_hidden_state(w, px, spec.mm_vision_select_layer, num_layers=spec.vit_layers)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(3):
+            O.vit_hidden_state(w, px, spec.mm_vision_select_layer, num_layers=spec.vit_layers)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_vit = e0.elapsed_time(e1) / 3
+        emb = torch.randn(1, S, spec.hidden_size, device=dev).to(dt)
+        cache = O.KVCache(spec.num_hidden_layers)
+        e0, e1 = ev(), ev()
+        e0.record()
+        h = O.llama_model(w, emb, cache, **kw)
+        tok = torch.nn.functional.linear(h[:, -1:], w["lm_head.weight"]).argmax(-1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_prefill = e0.elapsed_time(e1)
+
+        def step(tok):
+            x = torch.nn.functional.embedding(tok, w["model.embed_tokens.weight"])
+            hh = O.llama_model(w, x, cache, **kw)
+            return torch.nn.functional.linear(hh, w["lm_head.weight"]).argmax(-1)
+        for _ in range(3):
+            tok = step(tok)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(decode_tokens):
+            tok = step(tok)
+            int(tok)                                           # the reference syncs device->host every token (model_worker.py:390)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_dec = e0.elapsed_time(e1) / decode_tokens
+    del w
+    torch.cuda.empty_cache()
+    total = ms_vit + ms_prefill + N_NEW * ms_dec
+    return {"what": "oracle (eager torch ops, bf16) on the same B200", "tokens_per_s": N_NEW / (total / 1e3), "vit_frames_per_s": n_frames / (ms_vit / 1e3),
+            "prefill_ms": ms_prefill, "decode_ms_per_token": ms_dec, "decode_tokens_per_s": 1e3 / ms_dec}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,6 +272,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="videos per GPU (BASELINE config 3: --model valley-13b --batch 4 --new-tokens 256)")
     ap.add_argument("--new-tokens", type=int, default=128)
     ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--gpu-eager-baseline", action="store_true", help="also time the oracle as eager torch-CUDA ops on the GPU (SURVEY 8d)")
     a = ap.parse_args()
     global N_NEW, N_FRAMES
     N_NEW, N_FRAMES = a.new_tokens, a.frames
@@ -453,6 +507,8 @@ def main():
         for _ in range(3):
             PO.pil_pipeline(pre_host.numpy())
         line["cpu_baseline"]["preprocess_frames_per_s"] = 3 * N_FRAMES / (time.perf_counter() - t0)
+    if a.gpu_eager_baseline:
+        line["gpu_eager_baseline"] = gpu_eager_reference(spec, N_FRAMES)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

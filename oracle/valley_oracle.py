@@ -235,7 +235,7 @@ def rms_norm(x: Tensor, weight: Tensor, eps: float) -> Tensor:
 
 def rope_cos_sin(positions: Tensor, head_dim: int, theta: float, dtype) -> Tuple[Tensor, Tensor]:
     """HF:modeling_llama.py:107-135: inv_freq fp32, freqs = pos*inv_freq (fp32), cat, cos/sin, cast to x dtype."""
-    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).to(torch.float32) / head_dim))
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64, device=positions.device).to(torch.float32) / head_dim))
     freqs = (inv[None, :, None] @ positions[:, None, :].to(torch.float32)).transpose(1, 2)   # [B,S,hd/2]
     emb = torch.cat((freqs, freqs), dim=-1)
     return emb.cos().to(dtype), emb.sin().to(dtype)
@@ -301,15 +301,16 @@ def llama_model(w: Dict[str, Tensor], inputs_embeds: Tensor, cache: Optional[KVC
     layers, final RMSNorm."""
     B, S, H = inputs_embeds.shape
     past = cache.get_seq_length() if cache is not None else 0
-    pos = (past + torch.arange(S))[None, :].expand(B, -1)
+    dev = inputs_embeds.device          # (cpu in the tests; bench.py's eager-GPU baseline runs the same ops on cuda)
+    pos = (past + torch.arange(S, device=dev))[None, :].expand(B, -1)
     cos, sin = rope_cos_sin(pos, H // heads, theta, inputs_embeds.dtype)
     mask = None
     if S > 1 or attention_mask is not None:
         neg = torch.finfo(inputs_embeds.dtype).min
-        allowed = (torch.arange(past + S)[None, :] <= (past + torch.arange(S))[:, None])[None]      # [1,S,past+S]
+        allowed = (torch.arange(past + S, device=dev)[None, :] <= (past + torch.arange(S, device=dev))[:, None])[None]      # [1,S,past+S]
         if attention_mask is not None:
-            allowed = allowed & attention_mask[:, None, : past + S].bool()                            # [B,S,past+S]
-        mask = torch.zeros(allowed.shape, dtype=inputs_embeds.dtype).masked_fill(~allowed, neg)[:, None]
+            allowed = allowed & attention_mask[:, None, : past + S].bool().to(dev)                    # [B,S,past+S]
+        mask = torch.zeros(allowed.shape, dtype=inputs_embeds.dtype, device=dev).masked_fill(~allowed, neg)[:, None]
     x = inputs_embeds
     for i in range(n_layers):
         x = llama_layer(w, x, f"model.layers.{i}.", cos, sin, mask, cache, i, heads, eps)
