@@ -204,3 +204,45 @@ def test_checkpoint_directory_reader(tmp_path, fmt):
     assert len(checkpoint.weight_files(str(tmp_path))) == 2
     with pytest.raises(FileNotFoundError):
         checkpoint.weight_files(str(tmp_path / "clip"))
+
+
+def test_lora_adapter_is_merged_into_the_streamed_weights(tmp_path):
+    """run_valley.py:26-37 (merge_and_unload): W + (B @ A) * lora_alpha / r on the adapted projections, everything else untouched."""
+    import json
+    import os
+    from safetensors.torch import save_file
+    from valley_b200 import checkpoint
+    spec = syn.TINY
+    sd = syn.make_state_dict(spec, 0)
+    base = tmp_path / "base"
+    base.mkdir()
+    _write_checkpoint(str(base), spec, sd, "safetensors")
+    lora = tmp_path / "valley-lora"
+    lora.mkdir()
+    g = torch.Generator().manual_seed(9)
+    r, alpha, H, I = 16, 32, spec.hidden_size, spec.intermediate_size
+    targets = {"model.layers.0.self_attn.q_proj": (H, H), "model.layers.1.mlp.down_proj": (H, I), "model.layers.1.mlp.up_proj": (I, H)}
+    ad = {}
+    for mod, (o, i) in targets.items():
+        ad[f"base_model.model.{mod}.lora_A.weight"] = torch.randn(r, i, generator=g) * 0.05
+        ad[f"base_model.model.{mod}.lora_B.weight"] = torch.randn(o, r, generator=g) * 0.05
+    save_file(ad, str(lora / "adapter_model.safetensors"))
+    json.dump(dict(r=r, lora_alpha=alpha, base_model_name_or_path=str(base), target_modules=list(targets), peft_type="LORA"),
+              open(lora / "adapter_config.json", "w"))
+    assert checkpoint.is_lora_dir(str(lora)) and not checkpoint.is_lora_dir(str(base))
+    assert checkpoint.resolve_lora_base(str(lora)) == str(base)
+    merged = dict(checkpoint.iter_checkpoint_merged(str(base), str(lora)))
+    assert set(merged) == set(sd)
+    for name, w in sd.items():
+        mod = name[: -len(".weight")] if name.endswith(".weight") else None
+        if mod in targets:
+            want = w.double() + (ad[f"base_model.model.{mod}.lora_B.weight"].double() @ ad[f"base_model.model.{mod}.lora_A.weight"].double()) * (alpha / r)
+            assert torch.allclose(merged[name].double(), want, rtol=1e-5, atol=1e-6) and not torch.equal(merged[name], w)
+        else:
+            assert torch.equal(merged[name], w), name
+    # an adapter for a weight the base does not have is an error, not a silent no-op
+    ad["base_model.model.model.layers.7.self_attn.q_proj.lora_A.weight"] = torch.zeros(r, H)
+    ad["base_model.model.model.layers.7.self_attn.q_proj.lora_B.weight"] = torch.zeros(H, r)
+    save_file(ad, str(lora / "adapter_model.safetensors"))
+    with pytest.raises(KeyError):
+        list(checkpoint.iter_checkpoint_merged(str(base), str(lora)))

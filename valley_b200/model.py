@@ -242,9 +242,16 @@ class ValleyLlamaForCausalLM:
         local HF checkpoint directory (config.json + safetensors / .bin shards).  Weights are stored as bf16 whatever ``torch_dtype``
         says (fp16 checkpoints are converted on load)."""
         from . import checkpoint
-        cfg = ValleyConfig(**{**checkpoint.read_config(pretrained_model_name_or_path), **kw})
+        path = pretrained_model_name_or_path
+        if checkpoint.is_lora_dir(path):       # run_valley.py:26-37: PeftModel.from_pretrained(base, path).merge_and_unload()
+            base = checkpoint.resolve_lora_base(path)
+            cfg = ValleyConfig(**{**checkpoint.read_config(base), **kw})
+            m = cls(cfg, device)
+            m.load_state_dict(checkpoint.iter_checkpoint_merged(base, path, device=m.device))
+            return m
+        cfg = ValleyConfig(**{**checkpoint.read_config(path), **kw})
         m = cls(cfg, device)
-        m.load_state_dict(checkpoint.iter_checkpoint(pretrained_model_name_or_path))
+        m.load_state_dict(checkpoint.iter_checkpoint(path))
         return m
 
     @classmethod
