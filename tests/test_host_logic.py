@@ -246,3 +246,36 @@ def test_lora_adapter_is_merged_into_the_streamed_weights(tmp_path):
     save_file(ad, str(lora / "adapter_model.safetensors"))
     with pytest.raises(KeyError):
         list(checkpoint.iter_checkpoint_merged(str(base), str(lora)))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in valley_b200/_lib.py must have the layout gcc gives the structs of include/valley_b200.h
+    (a silent mismatch would scramble every config field / sampling parameter)."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    from valley_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"vly_config": _lib.VlyConfig, "vly_tokens": _lib.VlyTokens, "vly_sampling": _lib.VlySampling}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "valley_b200.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_probe"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l}
+    for cname, ct in structs.items():
+        assert got[(cname, "size")] == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert got[(cname, fname)] == getattr(ct, fname).offset, (cname, fname)
+    # enum values used across the boundary
+    assert (_lib.VLY_F32, _lib.VLY_BF16, _lib.VLY_F16) == (0, 1, 2)
+    assert _lib.POOLING == {"mean": 0, "max": 1, "temporal_importance": 2, "temporal_transformer": 3}
