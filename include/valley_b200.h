@@ -199,6 +199,13 @@ int vly_generate(vly_ctx* ctx, vly_kv* kv, const int64_t* first_tokens_dev, int 
 int vly_kernel_launch_count(vly_ctx* ctx, int64_t* out);   /* kernels launched by this ctx so far */
 int vly_num_sms(vly_ctx* ctx, int* out);
 
+/* in-kernel cycle counters of the last decode step / ViT attention launch, filled only when the process runs with VLY_MEGA_DBG=1 /
+ * VLY_ATTN_DBG=1 (tools/bench_decode.py, tools/bench_vit.py): copies n int64 values to host_out; returns 0, -1 (never enabled) or -2. */
+int vly_debug_mega_counters(long long* host_out, int n);
+int vly_debug_attn_counters(long long* host_out, int n);
+/* internal: lets the host-only translation units (host_splice.cpp, host_preprocess.cpp) set the thread-local error message */
+void vly_set_error_(const char* message);
+
 /* ---- low-level op hooks (per-kernel parity tests) ----
  * D[M,N] = epilogue(A[M,K] * W[N,K]^T): epi 0 bias->bf16, 3 bias+residual (in-place allowed)->bf16.  bias_dev fp32 or NULL. */
 int vly_test_gemm(vly_ctx* ctx, const void* a_dev, const void* w_dev, int M, int N, int K, int epi, const float* bias_dev,
