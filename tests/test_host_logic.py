@@ -279,3 +279,29 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     # enum values used across the boundary
     assert (_lib.VLY_F32, _lib.VLY_BF16, _lib.VLY_F16) == (0, 1, 2)
     assert _lib.POOLING == {"mean": 0, "max": 1, "temporal_importance": 2, "temporal_transformer": 3}
+
+
+def test_prompt_helpers_and_config_flags():
+    """Pure string / config logic of the reference surface (no GPU): valley_model.py:381-422, :40-52; model_worker.py:338-368."""
+    from valley_b200 import serving
+    from valley_b200.model import ValleyConfig, ValleyLlamaForCausalLM
+    # pooling variant selection: the later flag wins (valley_model.py:40-52 sets the attribute in that order)
+    assert ValleyConfig().patch_pooling_method == "mean"
+    assert ValleyConfig(use_patch_importance_pooling=True).patch_pooling_method == "temporal_importance"
+    assert ValleyConfig(use_patch_importance_pooling=True, use_delta_transformer=True).patch_pooling_method == "temporal_transformer"
+    with pytest.raises(ValueError):
+        ValleyConfig(patch_pooling_method="median")
+    assert ValleyConfig(some_hf_key=3).some_hf_key == 3                      # unknown HF config keys are kept, not rejected
+    # <video> expansion (model_worker.py:338-341)
+    p = serving.expand_video_prompt("a <video> b", 3, True)
+    assert p == "a <im_start>" + "<im_patch>" * 256 + "<im_end><vi_start>" + "<vi_frame>" * 3 + "<vi_end> b"
+    assert serving.expand_video_prompt("a <video> b", 3, False) == "a " + "<im_patch>" * 256 + " b"
+    # left truncation (model_worker.py:367-368)
+    ids = list(range(3000))
+    assert serving.truncate_source(ids, 2048, 256) == ids[-(2048 - 256 - 8):]
+    assert serving.truncate_source(ids[:100], 2048, 256) == ids[:100]
+    # process_response (valley_model.py:405-422) needs no model state
+    pr = ValleyLlamaForCausalLM.process_response
+    assert pr(None, ["### Assistant: hello there ### Human: x"]) == ["hello there"]
+    assert pr(None, ["Valley: Response: ok"]) == ["ok"]
+    assert pr(None, ["   plain"]) == ["plain"]
