@@ -305,3 +305,32 @@ def test_prompt_helpers_and_config_flags():
     assert pr(None, ["### Assistant: hello there ### Human: x"]) == ["hello there"]
     assert pr(None, ["Valley: Response: ok"]) == ["ok"]
     assert pr(None, ["   plain"]) == ["plain"]
+
+
+def test_splice_plan_and_oracle_match_the_reference_on_fuzzed_rows():
+    """400 random rows with well-formed / corrupted / truncated / misplaced <im_*> and <vi_*> blocks, each one pushed through the
+    LIVE reference by oracle/make_golden_splice_fuzz.py: the C host plan and the oracle must do exactly what the reference did --
+    same source map, or the same exception (type and message)."""
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_splice_fuzz.pt"))
+    spec, T = syn.TINY, g["T"]
+    tok, lib = Hh.oracle_tok(spec), _lib.load()
+    seen = {}
+    for i, (row, (kind, val)) in enumerate(zip(g["rows"], g["results"])):
+        seen[kind] = seen.get(kind, 0) + 1
+        code, smap, iidx = plan(row[None], T, vly_tokens(spec))
+        if kind == "plain":
+            assert code == 0 and int(iidx[0]) == -1 and bool((smap == -1).all()), i
+        elif kind == "map":
+            assert code == 0 and int(iidx[0]) == 0, (i, lib.vly_last_error())
+            assert torch.equal(smap[0], val), i
+            assert torch.equal(oracle_map(row, T, tok), val), i
+        elif kind == "ValueError":
+            assert code in (_lib.VLY_ERR_IM_COUNT, _lib.VLY_ERR_IM_CUT) and lib.vly_last_error().decode() == val, (i, code, val)
+            with pytest.raises(ValueError) as ei:
+                oracle_map(row, T, tok)
+            assert str(ei.value) == val, i
+        else:
+            assert kind == "IndexError" and code == _lib.VLY_ERR_INDEX, (i, code)
+            with pytest.raises(IndexError):
+                oracle_map(row, T, tok)
+    assert seen["map"] >= 40 and seen["ValueError"] >= 100 and seen["IndexError"] >= 10 and seen["plain"] >= 50
