@@ -127,3 +127,23 @@ def test_oracle_loss_matches_reference_fixture(name):
     with torch.no_grad():
         loss = O.causal_lm_loss(O.causal_lm_forward(sd, cfg, tok, ids, px, None), g["loss"]["labels"])
     assert torch.allclose(loss, g["loss"]["loss"], rtol=1e-5, atol=1e-6)
+
+
+def test_preprocess_oracle_equals_pillow_on_random_geometries():
+    """The numpy restatement against Pillow itself (the library the reference calls) on 40 random frame sizes, including
+    up-scaling, extreme aspect ratios and sizes next to the 256 / 224 thresholds: bit for bit, plus the host tables of the C ABI."""
+    import numpy as np
+    from oracle import preprocess_oracle as P
+    from valley_b200 import video
+    rs = np.random.RandomState(7)
+    sizes = [(int(rs.randint(30, 700)), int(rs.randint(30, 700))) for _ in range(34)] + [(256, 256), (257, 256), (224, 1000), (1000, 225), (31, 640), (256, 31)]
+    for h, w in sizes:
+        clip = rs.randint(0, 256, (1, h, w, 3)).astype(np.uint8)
+        a, b = P.preprocess_frames(clip), P.pil_pipeline(clip)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (h, w)
+        nh, nw, cy, cx = video.preprocess_plan(h, w)
+        assert (nh, nw) == P.resize_sizes(h, w) and (cy, cx) == P.crop_origin(nh, nw), (h, w)
+        for n_in, n_out in ((h, nh), (w, nw)):
+            k, xmin, cnt, kk = video.resample_coeffs(n_in, n_out)
+            ok, oxmin, ocnt, okk = P.bilinear_coeffs(n_in, n_out)
+            assert k == ok and np.array_equal(xmin, oxmin) and np.array_equal(cnt, ocnt) and np.array_equal(kk, okk), (h, w)
