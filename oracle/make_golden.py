@@ -212,6 +212,19 @@ def main():
                     mine = O.prepare_inputs_embeds(sd, cid, feats, tok)
                     close(mine, grabbed["e"], f"splice[{name}] inputs_embeds")
                     gold_splice[name] = dict(ids=cid, n_frames=cpx.shape[1], embeds_sub=grabbed["e"][:, :, ::8].clone())
+                # (e) images as a Python LIST of clips with different frame counts (valley_model.py:168-176, :187-188):
+                #     rows padded to one length with plain tokens; each sample's <vi_frame> count matches its own clip
+                if B >= 2:
+                    ra = syn.make_prompt_ids(spec, 1, 2, seed, len_b=25)[0]
+                    rb = syn.make_prompt_ids(spec, 1, 3, seed + 1, len_b=24)[0]
+                    lids = torch.stack([ra, rb])
+                    limgs = [px[0, :2], px[1, :3]]
+                    ref(lids, images=limgs, use_cache=False)
+                    lfeats = O.encode_images(sd, limgs, cfg.mm_vision_select_layer, num_layers=cfg.vit_layers)
+                    assert isinstance(lfeats, list) and lfeats[0].shape[0] == 2 and lfeats[1].shape[0] == 3
+                    mine = O.prepare_inputs_embeds(sd, lids, lfeats, tok)
+                    close(mine, grabbed["e"], "splice[list_images] inputs_embeds")
+                    gold_splice["list_images"] = dict(ids=lids, n_frames=[2, 3], embeds_sub=grabbed["e"][:, :, ::8].clone())
                 # error paths: same exception type + message from both
                 errs = {}
                 cut = base.clone()

@@ -131,8 +131,11 @@ def test_splice_golden_cases_and_errors_through_the_model():
     px = syn.make_pixels(g["B"], g["T"], g["seed"])
     fp32_sd = syn.make_state_dict(spec, g["seed"])
     for case, d in g["splice"].items():
-        cpx = px[:1, : d["n_frames"]]
-        emb = m.prepare_inputs_labels_for_multimodal(d["ids"].cuda(), None, None, None, cpx.cuda())[3]
+        if isinstance(d["n_frames"], list):          # images as a list of clips with different frame counts (valley_model.py:168-176)
+            cpx = [px[i, :n].cuda() for i, n in enumerate(d["n_frames"])]
+        else:
+            cpx = px[:1, : d["n_frames"]].cuda()
+        emb = m.prepare_inputs_labels_for_multimodal(d["ids"].cuda(), None, None, None, cpx)[3]
         ref = d["embeds_sub"]                       # the REFERENCE's own inputs_embeds (fp32 weights), sub-sampled
         assert Hh.rel_fro(emb[:, :, ::8], ref) < 2e-2, case
     for case, d in g["errors"].items():

@@ -42,7 +42,10 @@ def test_oracle_splice_cases_match_reference(name):
     px = syn.make_pixels(g["B"], g["T"], g["seed"])
     with torch.no_grad():
         for case, d in g["splice"].items():
-            cpx = px[:1, : d["n_frames"]]
+            if isinstance(d["n_frames"], list):          # images given as a list of clips with different frame counts
+                cpx = [px[i, :n] for i, n in enumerate(d["n_frames"])]
+            else:
+                cpx = px[:1, : d["n_frames"]]
             feats = O.encode_images(sd, cpx, cfg.mm_vision_select_layer, num_layers=cfg.vit_layers)
             emb = O.prepare_inputs_embeds(sd, d["ids"], feats, tok)
             assert torch.allclose(emb[:, :, ::8], d["embeds_sub"], rtol=1e-5, atol=1e-6), case
