@@ -637,6 +637,35 @@ def test_from_pretrained_checkpoint_directory(tmp_path):
     assert torch.equal(a, b)
 
 
+def test_long_prompt_near_the_context_limit():
+    """S = 1 800 of the 2 048-position context: 15 query tiles x up to 15 key tiles in the prefill attention, 29 KV splits per head in
+    the decode step; prefill last-token logits + teacher-forced decode steps vs the oracle, then generation up to the last position."""
+    spec, sd, m = get("tiny")
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    B, T, n = 2, 3, 4
+    ids, px = syn.make_prompt_ids(spec, B, T, 2, len_a=900, len_b=636), syn.make_pixels(B, T, 2)
+    assert ids.shape[1] == 1800
+    with torch.no_grad():
+        r_tok, r_log = O.greedy_generate(sd, cfg, tok, ids, px, n, return_logits=True)
+    m.logits_all_positions = False
+    try:
+        out = m(input_ids=ids.cuda(), images=px.cuda())
+    finally:
+        m.logits_all_positions = True
+    cache, logs = out.past_key_values, [out.logits[:, -1].cpu()]
+    for i in range(1, n):
+        o = m(input_ids=r_tok[:, i - 1:i].cuda(), past_key_values=cache)
+        logs.append(o.logits[:, -1].cpu())
+    logs = torch.stack(logs, 1)
+    check_close(logs, r_log, what="long prompt logits")
+    max_err = (logs - r_log).abs().max().item()
+    top2 = r_log.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * max_err
+    assert torch.equal(logs.argmax(-1)[safe], r_tok[safe])
+    full = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=1000)      # clipped to the room that is left
+    assert full.shape[1] == spec.max_position_embeddings and int(full.max()) < spec.vocab_size
+
+
 def test_cache_capacity_is_enforced():
     spec, sd, m = get("tiny")
     ids = syn.make_prompt_ids(spec, 1, 2, 0)
