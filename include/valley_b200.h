@@ -99,6 +99,10 @@ int vly_vit_encode_gather(vly_ctx* ctx, const void* pixels_dev, int pixel_dtype,
                           void* stream);
 /* enqueue after the kernels that read the gather buffer: lets the peers overwrite it in their next vly_vit_encode_gather */
 int vly_gather_release(vly_ctx* ctx, void* stream);
+/* A peer that never signals makes the device-side wait give up after ~10 s and raise a pinned flag in the context; from then on
+ * vly_vit_encode_gather / vly_gather_release / vly_gather_status return VLY_ERR_STATE (the buffer holds stale rows).  Call
+ * vly_gather_status after the synchronisation that follows a request (non-blocking read): *timed_out = 0 / 1. */
+int vly_gather_status(vly_ctx* ctx, int* timed_out);
 
 /* ---- frame preprocessing: what load_video does to the decoded uint8 frames before the vision tower
  * (valley/util/data_util.py:271-281): Resize(256) [PIL.Image.BILINEAR: video_transform.py:63-66 swaps the names] ->

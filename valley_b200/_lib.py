@@ -59,6 +59,7 @@ SIGNATURES = {
     "vly_gather_open_peers": (_i, [_vp, _vp, _i, _i]),
     "vly_vit_encode_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "vly_gather_release": (_i, [_vp, _vp]),
+    "vly_gather_status": (_i, [_vp, _p(_i)]),
     "vly_preprocess_plan": (_i, [_i, _i, _p(_i), _p(_i), _p(_i), _p(_i)]),
     "vly_resample_coeffs": (_i, [_i, _i, _p(_i), _p(C.c_int32), _p(C.c_int32), _p(C.c_int32)]),
     "vly_preprocess_frames": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -122,6 +122,7 @@ struct vly_ctx {
   bf16* g_peer_buf[8] = {};
   int* g_peer_flags[8] = {};
   int g_world = 0, g_rank = 0, g_epoch = 0;
+  int* g_timeout = nullptr;       // pinned + mapped: set by gather_wait_kernel when a peer never signalled; read by the host
   Buf w_xlocal;
   // pooling variants (valley_model.py:40-52, :205-213)
   float* pool_U = nullptr;                     // temporal_importance: W_proj^T w_pool, [256, vit_hidden] fp32
@@ -145,6 +146,8 @@ struct vly_kv {
   bf16* cache = nullptr;  // [L][2][B][nH][Smax][128]
   int host_len = 0;
   bool len_dirty = false;   // a stop token may have ended vly_generate early: host_len is re-read from the device on next use
+  int* h_len = nullptr;     // pinned: d_len is copied here on the generating stream, len_event marks the copy
+  cudaEvent_t len_event = nullptr;
   int* d_len = nullptr;   // device scalar
   int* d_step = nullptr;
   // decode workspace
@@ -176,10 +179,13 @@ struct vly_kv {
 };
 
 // after an eos-terminated vly_generate only the device knows how many steps ran (one blocking 4-byte read, off the hot path)
+// (the copy was enqueued on the stream that ran the generation -- torch streams are non-blocking, so a legacy-stream
+//  cudaMemcpy here would not be ordered after it)
 static int sync_len(vly_kv* kv) {
   if (!kv->len_dirty) return VLY_OK;
   CK(cudaSetDevice(kv->ctx->cfg.device));
-  CK(cudaMemcpy(&kv->host_len, kv->d_len, 4, cudaMemcpyDeviceToHost));
+  CK(cudaEventSynchronize(kv->len_event));
+  kv->host_len = *reinterpret_cast<volatile int*>(kv->h_len);
   kv->len_dirty = false;
   return VLY_OK;
 }
@@ -200,6 +206,22 @@ static int decode_mode() {
 static bool use_decode_v1() { return decode_mode() == 0; }
 
 static inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
+
+// cudaFuncSetAttribute is per DEVICE: a second vly_ctx on another GPU of the same process must opt in again, so what has been
+// set is tracked per (device, kernel) -- not in function-local statics.
+static std::mutex g_attr_mu;
+static std::map<std::pair<int, const void*>, size_t> g_attr_set;
+template <typename Kern>
+static int ensure_smem_attr(int device, Kern kern, size_t bytes, bool max_carveout = false) {
+  std::lock_guard<std::mutex> lk(g_attr_mu);
+  size_t& have = g_attr_set[std::make_pair(device, (const void*)kern)];
+  if (bytes > have || (have == 0 && max_carveout)) {
+    if (bytes > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (max_carveout) CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    have = bytes > 0 ? bytes : 1;
+  }
+  return VLY_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // TMA descriptors
@@ -237,11 +259,7 @@ static int make_tmap_3d(vly_ctx* c, CUtensorMap* m, const void* ptr, uint64_t d0
 template <int BN, int EPI>
 static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W, long long ldw, GemmParams p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  TRY(ensure_smem_attr(c->cfg.device, gemm_tc_kernel<BN, EPI>, Cfg::SMEM_BYTES));
   CUtensorMap ta, tb;
   TRY(make_tmap_2d(c, &ta, A, p.K, p.M, lda * 2, 64, 128));
   TRY(make_tmap_2d(c, &tb, W, p.K, p.N, ldw * 2, 64, BN));
@@ -256,11 +274,7 @@ static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W
     const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
     const bool use_cg2 = cg2_env >= 0 ? (cg2_env == 1) : (pair_tiles >= 2 * pairs);
     if (use_cg2) {
-      static bool attr2 = false;
-      if (!attr2) {
-        CK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr2 = true;
-      }
+      TRY(ensure_smem_attr(c->cfg.device, gemm_tc_kernel<BN, EPI, true>, Cfg::SMEM_BYTES));
       CUtensorMap tb2;
       TRY(make_tmap_2d(c, &tb2, W, p.K, p.N, ldw * 2, 64, BN / 2));
       cudaLaunchConfig_t cfg = {};
@@ -435,6 +449,7 @@ extern "C" void vly_destroy(vly_ctx* c) {
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  if (c->g_timeout) cudaFreeHost(c->g_timeout);
   delete c;
 }
 
@@ -724,11 +739,7 @@ static int launch_vit_attention(vly_ctx* c, const bf16* qkv, int F, bf16* out, c
   const vly_config& g = c->cfg;
   const int D = g.vit_hidden, tokens = (g.vit_image / g.vit_patch) * (g.vit_image / g.vit_patch) + 1;
   if (tokens != 257) return fail(VLY_ERR_INVALID, "vit attention kernel is specialised for 257 tokens (got %d)", tokens);
-  static bool attr = false;
-  if (!attr) {
-    CK(cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VitAttnCfg::SMEM_BYTES));
-    attr = true;
-  }
+  TRY(ensure_smem_attr(c->cfg.device, vit_attention_kernel, VitAttnCfg::SMEM_BYTES));
   CUtensorMap tq, tkv;
   TRY(make_tmap_2d(c, &tq, qkv, 3 * D, (uint64_t)F * tokens, (uint64_t)3 * D * 2, 64, 128));
   TRY(make_tmap_2d(c, &tkv, qkv, 3 * D, (uint64_t)F * tokens, (uint64_t)3 * D * 2, 64, 136));
@@ -749,11 +760,7 @@ static int launch_vit_attention(vly_ctx* c, const bf16* qkv, int F, bf16* out, c
   const int grid = items < c->num_sms ? items : c->num_sms;
   static const bool v1 = getenv("VLY_VIT_ATTN_V1") != nullptr;
   if (!v1) {
-    static bool attr2 = false;
-    if (!attr2) {
-      CK(cudaFuncSetAttribute(vit_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VitAttnPPCfg::SMEM_BYTES));
-      attr2 = true;
-    }
+    TRY(ensure_smem_attr(c->cfg.device, vit_attention_pp_kernel, VitAttnPPCfg::SMEM_BYTES));
     CUtensorMap tx;
     TRY(make_tmap_2d(c, &tx, qkv, 3 * D, (uint64_t)F * tokens, (uint64_t)3 * D * 2, 64, 1, /*swizzle128=*/false));   // single rows, read linearly
     vit_attention_pp_kernel<<<grid, VitAttnPPCfg::THREADS, VitAttnPPCfg::SMEM_BYTES, st>>>(tq, tx, p);
@@ -881,10 +888,29 @@ __global__ void gather_wait_kernel(volatile int* flags, int world, int epoch, in
   if ((int)threadIdx.x < world) {
     const long long t0 = clock64();
     while (flags[threadIdx.x] < epoch) {
-      if (clock64() - t0 > 20000000000LL) { *timeout_flag = 1; break; }   // ~10 s: a peer died
+      if (clock64() - t0 > 20000000000LL) {                               // ~10 s: a peer died
+        *reinterpret_cast<volatile int*>(timeout_flag) = 1;                // pinned host memory: the host sees it (gather_check_timeout)
+        break;
+      }
     }
     __threadfence_system();
   }
+}
+
+// A peer that never signals (dead / wedged rank) makes gather_wait_kernel give up after ~10 s and raise the context's pinned
+// timeout flag.  The gather buffer then holds partially written or previous-epoch rows, so every later gather call -- and
+// vly_gather_status, which callers poll after their next synchronisation -- fails loudly instead of decoding stale features.
+static int gather_check_timeout(vly_ctx* c, const char* who) {
+  if (c->g_timeout && *reinterpret_cast<volatile int*>(c->g_timeout) != 0)
+    return fail(VLY_ERR_STATE, "%s: a peer rank never signalled its frame features (fused all-gather timed out); the gather "
+                "buffer is stale -- the process group must be torn down", who);
+  return VLY_OK;
+}
+
+extern "C" int vly_gather_status(vly_ctx* c, int* timed_out) {
+  if (!c || !timed_out) return fail(VLY_ERR_INVALID, "vly_gather_status: null argument");
+  *timed_out = (c->g_timeout && *reinterpret_cast<volatile int*>(c->g_timeout) != 0) ? 1 : 0;
+  return *timed_out ? gather_check_timeout(c, "vly_gather_status") : VLY_OK;
 }
 
 extern "C" int vly_gather_create(vly_ctx* c, int64_t rows_total, void** local_buf, void* handle_out) {
@@ -899,6 +925,10 @@ extern "C" int vly_gather_create(vly_ctx* c, int64_t rows_total, void** local_bu
   c->g_buf = (bf16*)base;
   c->g_rows = rows_total;
   c->g_flags = (int*)((char*)base + data);
+  if (!c->g_timeout) {
+    CK(cudaHostAlloc((void**)&c->g_timeout, sizeof(int), cudaHostAllocMapped));
+    *c->g_timeout = 0;
+  }
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, base));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
@@ -934,6 +964,7 @@ extern "C" int vly_gather_release(vly_ctx* c, void* stream) {
   if (!c) return fail(VLY_ERR_INVALID, "null");
   std::lock_guard<std::mutex> lk(c->mu);
   if (c->g_world == 0) return fail(VLY_ERR_STATE, "vly_gather_release: no gather group");
+  TRY(gather_check_timeout(c, "vly_gather_release"));
   CK(cudaSetDevice(c->cfg.device));
   PeerFlags pf;
   for (int q = 0; q < 8; ++q) pf.p[q] = c->g_peer_flags[q] ? c->g_peer_flags[q] + 8 : nullptr;
@@ -952,8 +983,8 @@ extern "C" int vly_vit_encode_gather(vly_ctx* c, const void* pixels, int pixel_d
   if (((long long)frame_offset + F) * tokens > c->g_rows) return fail(VLY_ERR_INVALID, "vly_vit_encode_gather: frames [%d,%d) exceed the gather buffer", frame_offset, frame_offset + F);
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  static int* timeout_flag = nullptr;
-  if (!timeout_flag) { CK(cudaMalloc((void**)&timeout_flag, 4)); CK(cudaMemset(timeout_flag, 0, 4)); }
+  TRY(gather_check_timeout(c, "vly_vit_encode_gather"));
+  int* timeout_flag = c->g_timeout;
   if (c->g_epoch > 0) {   // every rank must have finished READING the previous epoch before anyone overwrites its buffer
     gather_wait_kernel<<<1, 32, 0, st>>>(c->g_flags + 8, c->g_world, c->g_epoch, timeout_flag);
     c->launches++;
@@ -1126,6 +1157,8 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   }
   kv->gemv_grid = 2 * c->num_sms;
   CK(cudaMalloc((void**)&kv->d_len, 8));
+  CK(cudaHostAlloc((void**)&kv->h_len, sizeof(int), cudaHostAllocDefault));
+  CK(cudaEventCreateWithFlags(&kv->len_event, cudaEventDisableTiming));
   kv->d_step = kv->d_len + 1;
   CK(cudaMemset(kv->d_len, 0, 8));
   CK(cudaMalloc((void**)&kv->x, (size_t)batch * H * 2));
@@ -1178,6 +1211,8 @@ extern "C" void vly_kv_destroy(vly_kv* kv) {
   cudaSetDevice(kv->ctx->cfg.device);
   if (kv->graph) cudaGraphExecDestroy(kv->graph);
   if (kv->graph_n) cudaGraphExecDestroy(kv->graph_n);
+  if (kv->h_len) cudaFreeHost(kv->h_len);
+  if (kv->len_event) cudaEventDestroy(kv->len_event);
   void* ps[] = {kv->d_sample, kv->key_bits, kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
   for (void* p : ps)
     if (p) cudaFree(p);
@@ -1260,11 +1295,7 @@ static int launch_gemv(vly_ctx* c, GemvParams p, int grid, cudaStream_t st) {
   if (grid > units) grid = units;
 #define VLY_GEMV_CASE(BM)                                                                                              \
   {                                                                                                                    \
-    static size_t max_set = 0;                                                                                         \
-    if (smem > max_set) {                                                                                              \
-      CK(cudaFuncSetAttribute(gemv_kernel<BM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      max_set = smem;                                                                                                  \
-    }                                                                                                                  \
+    TRY(ensure_smem_attr(c->cfg.device, gemv_kernel<BM, MODE>, smem));                                                 \
     gemv_kernel<BM, MODE><<<grid, 256, smem, st>>>(p);                                                                 \
   }
   if (bmax == 1) VLY_GEMV_CASE(1)
@@ -1313,13 +1344,8 @@ static int launch_gemv_ring(vly_ctx* c, GemvParams p, bool pdl, cudaStream_t st)
   cudaError_t e;
 #define VLY_RING_CASE(BM)                                                                                                   \
   {                                                                                                                         \
-    static size_t max_set = 0;                                                                                              \
-    if (smem > max_set) {                                                                                                   \
-      CK(cudaFuncSetAttribute(gemv_ring_kernel<BM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      /* keep the SM at its maximum shared-memory carve-out so the NEXT kernel's CTA can co-reside (PDL overlap) */      \
-      CK(cudaFuncSetAttribute(gemv_ring_kernel<BM, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));            \
-      max_set = smem;                                                                                                       \
-    }                                                                                                                       \
+    /* maximum shared-memory carve-out so the NEXT kernel's CTA can co-reside (PDL overlap) */                            \
+    TRY(ensure_smem_attr(c->cfg.device, gemv_ring_kernel<BM, MODE>, smem, true));                                           \
     e = launch_ex(gemv_ring_kernel<BM, MODE>, dim3(grid), dim3(RingCfg::THREADS), smem, st, pdl, p, n_stages);              \
   }
   if (bmax == 1) VLY_RING_CASE(1)
@@ -1339,12 +1365,8 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
   decode_embed_kernel<<<nb, 256, 0, st>>>(kv->cur_tokens + b0, c->embed, x, H, V);
   c->launches++;
   CKL();
-  static bool attn_attr = false;
   const size_t attn_smem = ((size_t)kv->Smax / kv->nsplit + 8) * 4;
-  if (!attn_attr && attn_smem > 40000) {
-    CK(cudaFuncSetAttribute(decode_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
-    attn_attr = true;
-  }
+  if (attn_smem > 40000) TRY(ensure_smem_attr(c->cfg.device, decode_attention_kernel, attn_smem));
   for (int l = 0; l < g.num_hidden_layers; ++l) {
     const LlamaLayerW& w = c->layers[l];
     bf16* kc = kv->k_layer(l) + (size_t)b0 * nH * kv->Smax * 128;
@@ -1371,11 +1393,7 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
         decode_attention_kernel<<<grid, 128, attn_smem, st>>>(p);
         CKL();
       } else {
-        static bool v2_attr = false;
-        if (!v2_attr) {
-          CK(cudaFuncSetAttribute(decode_attention_v2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-          v2_attr = true;
-        }
+        TRY(ensure_smem_attr(c->cfg.device, decode_attention_v2_kernel, 0, true));
         dim3 grid(nb * nH, kv->nsplit);
         CK(launch_ex(decode_attention_v2_kernel, grid, dim3(128), 0, st, true, p));
       }
@@ -1425,11 +1443,7 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
 static int launch_prefill_attention(vly_ctx* c, vly_kv* kv, const bf16* qbuf, int B, int S, int past, int layer, bf16* out, cudaStream_t st) {
   const vly_config& g = c->cfg;
   const int H = g.hidden_size, nH = g.num_attention_heads;
-  static bool attr = false;
-  if (!attr) {
-    CK(cudaFuncSetAttribute(llama_prefill_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PrefillAttnCfg::SMEM_BYTES));
-    attr = true;
-  }
+  TRY(ensure_smem_attr(c->cfg.device, llama_prefill_attention_kernel, PrefillAttnCfg::SMEM_BYTES));
   CUtensorMap tq, tk, tv;
   TRY(make_tmap_2d(c, &tq, qbuf, H, (uint64_t)B * S, (uint64_t)H * 2, 64, 128));
   TRY(make_tmap_3d(c, &tk, kv->k_layer(layer), 128, kv->Smax, (uint64_t)B * nH, 256, (uint64_t)kv->Smax * 256, 64, 128));
@@ -1587,11 +1601,7 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   cudaError_t e;
 #define VLY_MEGA_CASE(BM)                                                                                               \
   {                                                                                                                     \
-    static size_t max_set = 0;                                                                                          \
-    if (smem > max_set) {                                                                                               \
-      CK(cudaFuncSetAttribute(decode_step_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      max_set = smem;                                                                                                   \
-    }                                                                                                                   \
+    TRY(ensure_smem_attr(c->cfg.device, decode_step_kernel<BM>, smem));                                                 \
     e = cudaLaunchCooperativeKernel((void*)decode_step_kernel<BM>, dim3(c->num_sms), dim3(MegaCfg::THREADS), args, smem, st); \
   }
   if (bmax == 1) VLY_MEGA_CASE(1)
@@ -1727,7 +1737,11 @@ static int generate_impl(vly_ctx* c, vly_kv* kv, const int64_t* first_tokens, in
   if (steps_done_dev)      // (zeroed below, before the first step)
     CK(cudaMemcpyAsync(steps_done_dev, &kv->d_sample->steps_valid, 4, cudaMemcpyDeviceToDevice, st));
   kv->host_len += n_steps;
-  if (sp && (sp->eos_token_id >= 0 || sp->stop_token_id >= 0)) kv->len_dirty = true;      // the loop may have stopped early: the device holds the true length
+  if (sp && (sp->eos_token_id >= 0 || sp->stop_token_id >= 0)) {     // the loop may have stopped early: the device holds the true length
+    CK(cudaMemcpyAsync(kv->h_len, kv->d_len, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(kv->len_event, st));
+    kv->len_dirty = true;
+  }
   return VLY_OK;
 }
 

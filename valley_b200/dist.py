@@ -6,8 +6,10 @@ Every frame's ViT forward is independent (valley_model.py:179-184 loops over bat
 sequence's decode is independent, so the only exchange step is the gather of ``hidden_states[select]``
 shards ([F_local,257,1024] bf16) that lets each rank pool/splice the videos it decodes.
 
-``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is plumbing; the gather is not fused with
-the last ViT GEMM yet ("what comes next").
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is plumbing.  Two gather paths: ``FusedFrameGather`` (default on
+GPUs) -- the last ViT GEMM's epilogue stores every finished tile into every rank's gather buffer over NVLink peer memory, so
+compute and collective are one kernel -- and ``encode_frames_sharded`` (local ViT + one ``all_gather_into_tensor``), the plain
+baseline the fused path is checked against bit for bit (tests/test_gpu_multi.py, ``bench.py --gpus N``).
 """
 from __future__ import annotations
 
@@ -97,6 +99,14 @@ class FusedFrameGather:
         from ._lib import check
         check(self.model._lib.vly_gather_release(self.model._ctx, torch.cuda.current_stream().cuda_stream))
 
+    def check(self):
+        """Raise if a peer never delivered its rows (the device-side wait timed out): the buffer is stale.  Non-blocking read
+        of a pinned flag -- call it after the synchronisation that ends a request."""
+        import ctypes as C
+        from ._lib import check
+        flag = C.c_int(0)
+        check(self.model._lib.vly_gather_status(self.model._ctx, C.byref(flag)))
+
 
 def my_videos(n_videos: int, group=None) -> Tuple[int, int]:
     """Videos whose sequences this rank decodes (LLM replicated per GPU, batch sharded; no further collective)."""
@@ -122,6 +132,9 @@ def generate_sharded(model, input_ids: torch.Tensor, local_pixels: torch.Tensor,
     cache = model._borrow_cache(B)
     try:
         S = input_ids.shape[1]
-        return model._generate_with_cache(cache, input_ids, embeds, max_new_tokens, False, 1.0, None, None)[:, S:]
+        out = model._generate_with_cache(cache, input_ids, embeds, max_new_tokens, False, 1.0, None, None)[:, S:]
     finally:
         model._return_cache(cache)
+    if fused is not None:
+        fused.check()          # a timed-out gather of an EARLIER request is reported here at the latest (pinned flag, no sync)
+    return out

@@ -54,7 +54,7 @@ class ValleyConfig:
                  mm_vision_tower="openai/clip-vit-large-patch14", mm_hidden_size=1024, mm_vision_select_layer=-2,
                  use_mm_proj=True, mm_use_im_start_end=True, vit_layers=24, vit_heads=16, vit_mlp=4096, vit_patch=14,
                  vit_image=224, vit_eps=1e-5, use_patch_importance_pooling=False, use_delta_transformer=False,
-                 patch_pooling_method=None, **kw):
+                 patch_pooling_method=None, bos_token_id=1, eos_token_id=2, pad_token_id=None, **kw):
         self.hidden_size, self.num_hidden_layers = hidden_size, num_hidden_layers
         self.num_attention_heads, self.intermediate_size = num_attention_heads, intermediate_size
         self.vocab_size, self.rms_norm_eps, self.rope_theta = vocab_size, rms_norm_eps, rope_theta
@@ -71,6 +71,8 @@ class ValleyConfig:
         if patch_pooling_method not in _lib.POOLING:
             raise ValueError(f"patch_pooling_method {patch_pooling_method!r} not in {sorted(_lib.POOLING)}")
         self.patch_pooling_method = patch_pooling_method
+        # LlamaConfig defaults (HF:configuration_llama.py); HF generate() stops on config.eos_token_id unless told otherwise
+        self.bos_token_id, self.eos_token_id, self.pad_token_id = bos_token_id, eos_token_id, pad_token_id
         self.use_return_dict, self.use_cache = True, True
         self.output_attentions = self.output_hidden_states = False
         for k, v in kw.items():
@@ -85,7 +87,8 @@ class ValleyConfig:
                    mm_vision_select_layer=spec.mm_vision_select_layer, vit_layers=spec.vit_layers,
                    vit_heads=spec.vit_heads, vit_mlp=spec.vit_mlp, vit_patch=spec.vit_patch,
                    vit_image=spec.vit_image, vit_eps=spec.vit_eps,
-                   patch_pooling_method=getattr(spec, "patch_pooling_method", "mean"), **kw)
+                   patch_pooling_method=getattr(spec, "patch_pooling_method", "mean"),
+                   **{"eos_token_id": None, **kw})          # synthetic specs have no eos: random-init ids must not stop a run
 
 
 class CausalLMOutputWithPast(dict):
@@ -115,8 +118,12 @@ class ValleyKVCache:
 
     def __init__(self, model: "ValleyLlamaForCausalLM", batch: int, max_seq: int):
         self._model, self.batch, self.max_seq = model, batch, max_seq
-        h = C.c_void_p()
-        check(model._lib.vly_kv_create(model._ctx, batch, max_seq, C.byref(h)))
+        h = model._pop_handle(batch, max_seq)            # a handle (allocation + captured CUDA graph) freed by an earlier cache
+        if h is None:
+            h = C.c_void_p()
+            check(model._lib.vly_kv_create(model._ctx, batch, max_seq, C.byref(h)))
+        else:
+            check(model._lib.vly_kv_reset(h, _stream()))
         self._h = h
 
     def get_seq_length(self, layer_idx: int = 0) -> int:
@@ -159,25 +166,88 @@ class ValleyKVCache:
         check(self._model._lib.vly_kv_set_key_mask(self._h, m.data_ptr(), total_len, _stream()))
 
     def __del__(self):
+        # forward() without past_key_values hands a fresh cache to the caller on every request (model_worker.py:371-379);
+        # when the caller drops it, the allocation (1 GB / sequence at 7B) goes back to the model instead of to cudaFree
         try:
             if getattr(self, "_h", None) is not None and self._model._ctx:
-                self._model._lib.vly_kv_destroy(self._h)
+                if not self._model._push_handle(self.batch, self.max_seq, self._h):
+                    self._model._lib.vly_kv_destroy(self._h)
                 self._h = None
         except Exception:
             pass
 
 
-class _VisionTower:
+def _same_device(have: torch.device, want) -> bool:
+    want = torch.device(want) if not isinstance(want, torch.device) else want
+    return want.type == "cuda" and (want.index is None or want.index == have.index)
+
+
+class _ModuleSurface:
+    """The slice of ``nn.Module`` the reference's callers touch on the model and on ``vision_tower``
+    (model_worker.py:78,86; run_valley.py:42-43; run_valley_conv.py:113,126): ``.to()``, ``.cuda()``, ``.half()``,
+    ``.eval()``, ``.device``, ``.dtype``.  Weights live packed (bf16) inside the library on the device chosen at
+    construction, so these calls VALIDATE and return self: a 16-bit float dtype is accepted (fp16 checkpoints were
+    converted to bf16 at load), the owning CUDA device is accepted, anything else raises -- there is no CPU path."""
+    device: torch.device
+    dtype = torch.bfloat16
+    training = False
+
+    def to(self, *args, **kwargs):
+        device, dtype = kwargs.get("device"), kwargs.get("dtype")
+        for a in args:
+            if isinstance(a, torch.dtype):
+                dtype = a
+            elif isinstance(a, (str, torch.device, int)):
+                device = a
+            elif torch.is_tensor(a):
+                device, dtype = a.device, a.dtype
+        if device is not None:
+            device = f"cuda:{device}" if isinstance(device, int) else device
+            if not _same_device(self.device, device):
+                raise _lib.VlyError(f"valley_b200 weights live on {self.device}; .to({device!r}) is not supported "
+                                    "(there is no CPU path; build the model with device=... instead)")
+        if dtype is not None and dtype not in (torch.float16, torch.bfloat16):
+            raise _lib.VlyError(f".to({dtype}): the packed weights are bf16; only 16-bit float dtypes are accepted")
+        return self
+
+    def cuda(self, device=None):
+        return self.to(device="cuda" if device is None else device)
+
+    def half(self):
+        return self.to(dtype=torch.float16)
+
+    def bfloat16(self):
+        return self.to(dtype=torch.bfloat16)
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise _lib.VlyError("valley_b200 is the inference hot path: forward only (SURVEY 8 f-4), no train() mode")
+        return self.eval()
+
+    def requires_grad_(self, requires_grad: bool = False):
+        if requires_grad:
+            raise _lib.VlyError("valley_b200 holds no autograd parameters")
+        return self
+
+
+class _VisionTower(_ModuleSurface):
     """Stands where CLIPVisionModel sits on the reference model: carries ``.config`` with the sentinel ids
-    (run_valley.py:13-18, model_worker.py:80-84) and is callable like the reference's use of it."""
+    (run_valley.py:13-18, model_worker.py:80-84), takes the ``.to(device, dtype)`` the callers issue
+    (model_worker.py:78, run_valley_conv.py:126) and is callable like the reference's use of it."""
 
     def __init__(self, model: "ValleyLlamaForCausalLM"):
         self._model = model
+        self.device = model.device
         cfg = model.config
         self.config = types.SimpleNamespace(
             hidden_size=cfg.mm_hidden_size, image_size=cfg.vit_image, patch_size=cfg.vit_patch,
             num_hidden_layers=cfg.vit_layers, use_im_start_end=cfg.mm_use_im_start_end,
-            im_patch_token=-1, im_start_token=-1, im_end_token=-1)
+            im_patch_token=-1, im_start_token=-1, im_end_token=-1,
+            _name_or_path=getattr(cfg, "mm_vision_tower", None))
 
     def __call__(self, pixel_values: torch.Tensor, output_hidden_states: bool = True, select_layer: Optional[int] = None):
         sel = self._model.config.mm_vision_select_layer if select_layer is None else select_layer
@@ -185,24 +255,78 @@ class _VisionTower:
         return types.SimpleNamespace(selected_hidden_state=hs, select_layer=sel)
 
 
-class ValleyLlamaModel:
+class _PackedLinear(_ModuleSurface):
+    """Shape-carrying stand-in for an ``nn.Linear`` / ``nn.Embedding`` whose weight lives packed inside the library
+    (fused / norm-folded / interleaved -- there is no per-module weight tensor to hand out)."""
+
+    def __init__(self, owner, **dims):
+        self.device = owner.device
+        for k, v in dims.items():
+            setattr(self, k, v)
+
+    @property
+    def weight(self):
+        raise _lib.VlyError("weights are packed inside libvalley_b200.so (fused QKV, norm-folded, RoPE-interleaved); "
+                            "load them with load_state_dict / from_pretrained -- they cannot be read back per module")
+
+
+class ValleyLlamaModel(_ModuleSurface):
     """valley_model.py:21-254.  Holds the vision tower handle; ``forward`` returns final hidden states is NOT exposed
-    separately (the final RMSNorm is folded into lm_head) -- callers in the reference only use the CausalLM wrapper."""
+    separately (the final RMSNorm is folded into lm_head) -- callers in the reference only use the CausalLM wrapper.
+    Plain attributes the callers set on it (``multi_image``, ``multi_image_mode``: model_worker.py:63-64 -- never read by
+    the reference either) are accepted like on any Python object."""
 
     def __init__(self, owner: "ValleyLlamaForCausalLM"):
         self._owner = owner
+        self.device = owner.device
         self.config = owner.config
         self.vision_tower = _VisionTower(owner)
         self.patch_pooling_method = owner.config.patch_pooling_method      # valley_model.py:27, :40-52
-        self.mm_projector = types.SimpleNamespace(in_features=owner.config.mm_hidden_size,
-                                                  out_features=owner.config.hidden_size)
-        self.embed_tokens = types.SimpleNamespace(num_embeddings=owner.config.vocab_size,
-                                                  embedding_dim=owner.config.hidden_size)
+        self.mm_projector = _PackedLinear(owner, in_features=owner.config.mm_hidden_size, out_features=owner.config.hidden_size)
+        self.embed_tokens = _PackedLinear(owner, num_embeddings=owner.config.vocab_size, embedding_dim=owner.config.hidden_size)
 
 
-class ValleyLlamaForCausalLM:
+class KeywordsStoppingCriteria:
+    """valley/util/data_util.py:40-56 (a ``transformers.StoppingCriteria``): stop when the text decoded from the ids generated
+    so far contains a keyword.  Same quirk as the reference: the FIRST call only records the prompt length (so the first
+    generated token is never tested on its own), later calls decode row 0 of ``output_ids[:, start_len:]``."""
+
+    def __init__(self, keywords, tokenizer, input_ids):
+        self.keywords = keywords
+        self.tokenizer = tokenizer
+        self.start_len = None
+        self.input_ids = input_ids
+
+    def __call__(self, output_ids, scores=None, **kwargs) -> bool:
+        if self.start_len is None:
+            self.start_len = self.input_ids.shape[1]
+        else:
+            outputs = self.tokenizer.batch_decode(output_ids[:, self.start_len:], skip_special_tokens=True)[0]
+            for keyword in self.keywords:
+                if keyword in outputs:
+                    return True
+        return False
+
+
+_UNSET = object()
+
+
+def _open_video_reader(path: str):
+    """Default file reader of ``completion(tokenizer, path, ...)``: decord, exactly as load_video opens it
+    (data_util.py:258-260).  Container decoding is CPU work outside the hot path; inject another reader factory through
+    ``model.video_reader_factory`` (anything with ``len()``, ``get_batch(idx)`` -> [n,H,W,3] uint8, ``get_avg_fps()``)."""
+    try:
+        import decord
+    except ImportError as e:
+        raise ImportError("completion() was given a video path but decord is not installed; set model.video_reader_factory "
+                          "to a callable path -> reader, or pass the decoded clip tensor [3,T,224,224]") from e
+    return decord.VideoReader(path, num_threads=1, ctx=decord.cpu(0))
+
+
+class ValleyLlamaForCausalLM(_ModuleSurface):
     """valley_model.py:257-439 behind libvalley_b200.so."""
     config_class = ValleyConfig
+    video_reader_factory = staticmethod(_open_video_reader)
 
     def __init__(self, config: ValleyConfig, device: Union[int, str, torch.device] = 0):
         self._lib = _lib.load()
@@ -226,15 +350,33 @@ class ValleyLlamaForCausalLM:
         self.logits_all_positions = True      # reference behaviour (valley_model.py:304-305); generate() uses last-only
         import threading
         self._cache_pool, self._pool_lock = {}, threading.Lock()
+        self._free_handles = {}               # (batch, max_seq) -> [vly_kv handles] released by dropped ValleyKVCache objects
 
     # ---------------- lifetime / weights ----------------
     def __del__(self):
         try:
             if getattr(self, "_ctx", None):
+                for lst in getattr(self, "_free_handles", {}).values():
+                    for h in lst:
+                        self._lib.vly_kv_destroy(h)
+                self._free_handles = {}
                 self._lib.vly_destroy(self._ctx)
                 self._ctx = None
         except Exception:
             pass
+
+    def _pop_handle(self, batch: int, max_seq: int):
+        with self._pool_lock:
+            lst = self._free_handles.get((batch, max_seq))
+            return lst.pop() if lst else None
+
+    def _push_handle(self, batch: int, max_seq: int, h) -> bool:
+        with self._pool_lock:
+            lst = self._free_handles.setdefault((batch, max_seq), [])
+            if len(lst) >= 2:
+                return False
+            lst.append(h)
+            return True
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype=None, device=0, **kw) -> "ValleyLlamaForCausalLM":
@@ -281,9 +423,35 @@ class ValleyLlamaForCausalLM:
     def get_model(self) -> ValleyLlamaModel:      # valley_model.py:269
         return self.model
 
-    def eval(self):
-        self.training = False
-        return self
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return _PackedLinear(self, in_features=self.config.hidden_size, out_features=self.config.vocab_size)
+
+    def resize_token_embeddings(self, new_num_tokens: Optional[int] = None):
+        """Growing the embedding table is a training-time step (train.py:147 -> initialize_vision_tokenizer); released
+        checkpoints already contain the added tokens.  Accepted as a no-op when nothing has to grow."""
+        if new_num_tokens is not None and new_num_tokens > self.config.vocab_size:
+            raise _lib.VlyError(f"resize_token_embeddings({new_num_tokens}) > loaded vocab {self.config.vocab_size}: growing the "
+                                "embeddings is a training-time operation; load a checkpoint that already holds the added tokens")
+        return self.model.embed_tokens
+
+    def initialize_vision_tokenizer(self, tokenizer):
+        """valley_model.py:354-379 for an inference checkpoint: register the sentinel tokens with the tokenizer and record
+        their ids on ``vision_tower.config``.  The reference also grows the embeddings and initialises the new rows with the
+        mean embedding -- that is checkpoint construction (training); here the tokenizer must fit the loaded vocabulary."""
+        vc = self.get_model().vision_tower.config
+        vc.use_im_start_end = True
+        tokenizer.add_tokens([DEFAULT_IMAGE_PATCH_TOKEN, DEFAULT_VIDEO_FRAME_TOKEN], special_tokens=True)
+        self.resize_token_embeddings(len(tokenizer))
+        tokenizer.add_tokens([DEFAULT_IM_START_TOKEN, DEFAULT_IM_END_TOKEN, DEFAULT_VI_START_TOKEN, DEFAULT_VI_END_TOKEN],
+                             special_tokens=True)
+        self.resize_token_embeddings(len(tokenizer))
+        vc.im_start_token, vc.im_end_token = tokenizer.convert_tokens_to_ids([DEFAULT_IM_START_TOKEN, DEFAULT_IM_END_TOKEN])
+        vc.vi_start_token, vc.vi_end_token = tokenizer.convert_tokens_to_ids([DEFAULT_VI_START_TOKEN, DEFAULT_VI_END_TOKEN])
+        vc.vi_frame_token = tokenizer.convert_tokens_to_ids(DEFAULT_VIDEO_FRAME_TOKEN)
+        vc.im_patch_token = tokenizer.convert_tokens_to_ids([DEFAULT_IMAGE_PATCH_TOKEN])[0]
 
     def launches(self) -> int:
         n = C.c_int64()
@@ -454,6 +622,10 @@ class ValleyLlamaForCausalLM:
         (the reference returns them in the model dtype; callers .float() them).  A 2-D attention_mask [B, past+S] masks
         keys exactly as HF does (padding mask AND causal mask; position ids are not shifted -- the reference never
         passes position_ids); rows that are themselves padding produce unspecified (finite) logits."""
+        if output_hidden_states or output_attentions:
+            # valley_model.py:285-300 forwards these to LlamaModel; the fused path never materialises per-layer hidden states
+            # or attention probabilities (that is the point of it), so asking for them is an error rather than a silent None
+            raise NotImplementedError("output_hidden_states / output_attentions are not produced by the fused kernels")
         if inputs_embeds is None:
             if input_ids is None:
                 raise ValueError("You have to specify either input_ids or inputs_embeds")
@@ -505,22 +677,35 @@ class ValleyLlamaForCausalLM:
 
     @torch.no_grad()
     def generate(self, input_ids=None, images=None, max_new_tokens: int = 1024, do_sample: bool = False,
-                 temperature: float = 1.0, stopping_criteria=None, eos_token_id: Optional[int] = None, **kw):
+                 temperature: float = 1.0, stopping_criteria=None, eos_token_id=_UNSET, **kw):
         """Greedy (or temperature) generation == the loop of model_worker.py:371-397 / HF generate as called at
-        valley_model.py:432.  Returns [B, S + n_new] like HF.  With no stopping criteria, greedy decoding runs
+        valley_model.py:432.  Returns [B, S + n_new] like HF.  With no stopping criteria, decoding runs
         entirely on the device (CUDA-graph replay, no per-token host sync).  ``attention_mask`` [B, S] (left padding)
-        is honoured like HF generate does; generated positions are always attendable."""
+        is honoured like HF generate does; generated positions are always attendable.
+
+        HF defaults that the reference's callers rely on are kept: ``eos_token_id`` / ``pad_token_id`` default to the config's
+        (generation stops when every row has emitted eos; finished rows are padded), and when no ``attention_mask`` is given
+        but the prompt contains ``pad_token_id`` (!= eos) the mask is inferred as ``input_ids != pad_token_id``
+        (HF:generation/utils.py _prepare_attention_mask_for_generation).  Pass ``eos_token_id=None`` to run the full length."""
         B, S = input_ids.shape
         room = self.config.max_position_embeddings - S
         n_new = max(0, min(max_new_tokens, room))
         if n_new == 0:
             return input_ids.to(self.device)
+        if eos_token_id is _UNSET:
+            eos_token_id = getattr(self.config, "eos_token_id", None)
+        pad_token_id = kw.get("pad_token_id", getattr(self.config, "pad_token_id", None))
+        attention_mask = kw.get("attention_mask")
+        if attention_mask is None and pad_token_id is not None and (eos_token_id is None or pad_token_id != eos_token_id):
+            is_pad = input_ids == pad_token_id
+            if bool(is_pad.any()):
+                attention_mask = (~is_pad).to(torch.int64)
         _, _, _, embeds, _ = self.prepare_inputs_labels_for_multimodal(input_ids, None, None, None, images)
         cache = self._borrow_cache(B)
         try:
-            cache.set_attention_mask(kw.get("attention_mask"), S)
+            cache.set_attention_mask(attention_mask, S)
             return self._generate_with_cache(cache, input_ids, embeds, n_new, do_sample, temperature, stopping_criteria, eos_token_id,
-                                             kw.get("pad_token_id"))
+                                             pad_token_id)
         finally:
             self._return_cache(cache)
 
@@ -559,14 +744,20 @@ class ValleyLlamaForCausalLM:
                 out[:, 1:] = rest
                 n_valid += int(done.item())
             return torch.cat([ids_dev, out[:, :n_valid]], dim=1)
-        # host-visible loop (stopping criteria / sampling / eos): one device->host sync per token, as in the reference
+        # host-visible loop (stopping criteria present, or B > 64): one device->host sync per token, as in the reference.
+        # HF semantics per row: a row that has emitted eos is finished and is fed / emits pad from then on
         seq = ids_dev
+        finished = torch.zeros(B, dtype=torch.bool, device=self.device)
+        pad = int(pad_token_id) if pad_token_id is not None else (int(eos_token_id) if eos_token_id is not None else 0)
         for i in range(n_new):
             if not greedy:
                 probs = torch.softmax(logits[:, -1, :] / temperature, dim=-1)    # model_worker.py:393-394
                 nxt = torch.multinomial(probs, num_samples=1).reshape(B)
+            if eos_token_id is not None:
+                nxt = torch.where(finished, torch.full_like(nxt, pad), nxt)
+                finished = finished | (nxt == eos_token_id)
             seq = torch.cat([seq, nxt[:, None]], dim=1)
-            if eos_token_id is not None and bool((nxt == eos_token_id).all()):
+            if eos_token_id is not None and bool(finished.all()):
                 break
             if stopping_criteria and any(sc(seq, None) for sc in stopping_criteria):
                 break
@@ -613,14 +804,34 @@ class ValleyLlamaForCausalLM:
 
     @torch.no_grad()
     def completion(self, tokenizer, video, message: list, gen_kwargs: dict, device=None):
-        """valley_model.py:424-439.  ``video`` is a [3,T,224,224] tensor (what load_video returns) -- decoding a file
-        with decord is outside the hot path."""
+        """valley_model.py:424-439, same call: ``model.completion(tokenizer, args.video_file, message, gen_kwargs, device)``
+        (run_valley.py:56).  ``video`` is a file path -- opened by ``self.video_reader_factory`` (decord by default, as
+        load_video does; container decoding is CPU work outside the hot path) and then sampled (8 frames, 'fixed'),
+        resized, cropped and normalised ON THE DEVICE, bit-identical to load_video (valley_b200/video.py) -- or the decoded
+        clip tensor [3,T,224,224] load_video would have returned.  Generation stops like the reference's: the
+        ``KeywordsStoppingCriteria(['###'])`` it passes (:431-432) plus HF generate's default stop on ``config.eos_token_id``
+        (overridable through ``gen_kwargs``)."""
         inputs = self.build_inputs(tokenizer, message)
         input_ids = torch.as_tensor(inputs.input_ids).to(self.device)
-        if not torch.is_tensor(video):
-            raise TypeError("completion() takes the decoded clip tensor [3,T,224,224]; file decoding is out of scope")
-        images = video.permute(1, 0, 2, 3).unsqueeze(0).half().to(self.device)
-        output_ids = self.generate(input_ids=input_ids, images=images, **gen_kwargs)
-        n_in = input_ids.shape[1]
-        outputs = tokenizer.batch_decode(output_ids[:, n_in:], skip_special_tokens=True)
+        if torch.is_tensor(video):
+            images = video.permute(1, 0, 2, 3).unsqueeze(0).half().to(self.device)
+        else:
+            from . import video as _video
+            reader = self.video_reader_factory(str(video))
+            images = _video.load_video(self, reader, "fixed", 8, dtype=torch.float16).unsqueeze(0)      # [1,T,3,224,224]
+        gen_kwargs = dict(gen_kwargs)
+        if "attention_mask" not in gen_kwargs and getattr(inputs, "attention_mask", None) is not None:
+            am = torch.as_tensor(inputs.attention_mask)
+            if bool((am == 0).any()):               # build_inputs pads on the left (valley_model.py:400-402); B == 1 -> no padding
+                gen_kwargs["attention_mask"] = am
+        if "eos_token_id" not in gen_kwargs and getattr(tokenizer, "eos_token_id", None) is not None \
+                and getattr(self.config, "eos_token_id", None) is None:
+            gen_kwargs["eos_token_id"] = tokenizer.eos_token_id
+        stopping_criteria = KeywordsStoppingCriteria(['###'], tokenizer, input_ids)
+        output_ids = self.generate(input_ids=input_ids, images=images, stopping_criteria=[stopping_criteria], **gen_kwargs)
+        input_token_len = input_ids.shape[1]
+        n_diff_input_output = (input_ids != output_ids[:, :input_token_len]).sum().item()
+        if n_diff_input_output > 0:
+            print(f'[Warning] {n_diff_input_output} output_ids are not the same as the input_ids')
+        outputs = tokenizer.batch_decode(output_ids[:, input_token_len:], skip_special_tokens=True)
         return self.process_response(outputs)
