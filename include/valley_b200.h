@@ -97,6 +97,10 @@ int vly_gather_create(vly_ctx* ctx, int64_t rows_total, void** local_buf_dev, vo
 int vly_gather_open_peers(vly_ctx* ctx, const void* handles_64B_each, int world, int rank);
 int vly_vit_encode_gather(vly_ctx* ctx, const void* pixels_dev, int pixel_dtype, int n_frames, int frame_offset, int select_layer,
                           void* stream);
+/* the same with the local frames dealt round-robin: local frame i is global frame frame_offset + i * frame_stride (frame_stride =
+ * world size, frame_offset = rank), so every video's frames are spread over all ranks and every rank needs remote frames */
+int vly_vit_encode_gather_strided(vly_ctx* ctx, const void* pixels_dev, int pixel_dtype, int n_frames, int frame_offset,
+                                  int frame_stride, int select_layer, void* stream);
 /* enqueue after the kernels that read the gather buffer: lets the peers overwrite it in their next vly_vit_encode_gather */
 int vly_gather_release(vly_ctx* ctx, void* stream);
 /* A peer that never signals makes the device-side wait give up after ~10 s and raise a pinned flag in the context; from then on

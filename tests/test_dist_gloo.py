@@ -17,6 +17,9 @@ def test_shard_bounds_cover_and_balance():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1 and sizes == vdist.all_shard_sizes(n, w)
+            dealt = [list(vdist.dealt_frames(n, w, r)) for r in range(w)]
+            assert sorted(sum(dealt, [])) == list(range(n)) and [len(d) for d in dealt] == vdist.dealt_sizes(n, w)
+            assert max(map(len, dealt)) - min(map(len, dealt)) <= 1
 
 
 def _worker(rank, world, port, n_frames, q):
@@ -29,6 +32,9 @@ def _worker(rank, world, port, n_frames, q):
         got = vdist.encode_frames_sharded(fake_encode, full[lo:hi], n_frames)
         want = fake_encode(full)
         ok = torch.equal(got, want)
+        mine = list(vdist.dealt_frames(n_frames, world, rank))              # round-robin dealing: every rank needs remote frames
+        got_i = vdist.encode_frames_sharded(fake_encode, full[mine], n_frames, interleaved=True)
+        ok = ok and torch.equal(got_i, want)
         vl, vh = vdist.my_videos(5)
         q.put((rank, ok, (vl, vh)))
     finally:

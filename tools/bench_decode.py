@@ -35,11 +35,15 @@ print(f"{a.model} B={a.batch}: {best:.3f} ms/token  {a.batch / best * 1e3:.1f} t
       f"env V1={os.environ.get('VLY_DECODE_V1')} NO_PDL={os.environ.get('VLY_NO_PDL')}  tokens[0,:6]={out[0,:6].tolist()}")
 if os.environ.get("VLY_MEGA_DBG"):
     import ctypes as C
-    buf = (C.c_longlong * (148 * 8))()
-    rc = m._lib.vly_debug_mega_counters(buf, 148 * 8)
+    buf = (C.c_longlong * (148 * 32))()
+    rc = m._lib.vly_debug_mega_counters(buf, 148 * 32)
     import numpy as np
-    arr = np.array(buf[:]).reshape(148, 8)
-    names = ["grid sync", "stage x", "weight loop", "attention", "  (of loop: wait full)"]
-    print("per-step cycle breakdown (mean over CTAs | min | max), SM clock cycles:")
+    arr = np.array(buf[:]).reshape(148, 32)
+    names = ["grid sync", "stage x", "weight loop", "attention"]
+    print("last step, cycle breakdown (mean over CTAs | min | max), SM clock cycles (~1.9 GHz):")
     for i, nme in enumerate(names):
         print(f"  {nme:24s} {arr[:, i].mean():12.0f} {arr[:, i].min():12d} {arr[:, i].max():12d}")
+    print("  per phase type: stage-x | loop | trailing grid sync   (mean over CTAs, us at 1.9 GHz; [min..max] of loop)")
+    for t, nme in enumerate(["QKV", "ATTN", "OPROJ", "GATEUP", "DOWN", "LOGITS"]):
+        a = arr[:, 8 + 3 * t: 11 + 3 * t] / 1.9e3
+        print(f"  {nme:8s} {a[:, 0].mean():9.1f} {a[:, 1].mean():9.1f} {a[:, 2].mean():9.1f}   [{a[:, 1].min():.1f} .. {a[:, 1].max():.1f}]")

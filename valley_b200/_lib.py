@@ -58,6 +58,7 @@ SIGNATURES = {
     "vly_gather_create": (_i, [_vp, _i64, _p(_vp), _vp]),
     "vly_gather_open_peers": (_i, [_vp, _vp, _i, _i]),
     "vly_vit_encode_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "vly_vit_encode_gather_strided": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vly_gather_release": (_i, [_vp, _vp]),
     "vly_gather_status": (_i, [_vp, _p(_i)]),
     "vly_preprocess_plan": (_i, [_i, _i, _p(_i), _p(_i), _p(_i), _p(_i)]),

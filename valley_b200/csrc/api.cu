@@ -782,16 +782,16 @@ static int vit_layers_needed(const vly_config& g, int select_layer, int* out) {
 }
 
 static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int select_layer, void* out_dev, void* stream,
-                           bool gather, long long gather_row_off);
+                           bool gather, long long gather_frame_off, int gather_frame_stride);
 
 extern "C" int vly_vit_encode(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int select_layer, void* out_dev, void* stream) {
   if (!c || !pixels || !out_dev || F <= 0) return fail(VLY_ERR_INVALID, "vly_vit_encode: bad argument");
   std::lock_guard<std::mutex> lk(c->mu);
-  return vit_encode_impl(c, pixels, pixel_dtype, F, select_layer, out_dev, stream, false, 0);
+  return vit_encode_impl(c, pixels, pixel_dtype, F, select_layer, out_dev, stream, false, 0, 1);
 }
 
 static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int select_layer, void* out_dev, void* stream,
-                           bool gather, long long gather_row_off) {
+                           bool gather, long long gather_frame_off, int gather_frame_stride) {
   if (!c->finalized || !c->has_vit) return fail(VLY_ERR_STATE, "vly_vit_encode: vision weights not loaded/finalised");
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -866,7 +866,9 @@ static int vit_encode_impl(vly_ctx* c, const void* pixels, int pixel_dtype, int 
         if (gather && l == n_layers - 1) {
           p.n_peers = c->g_world;
           for (int q = 0; q < c->g_world; ++q) p.peer_out[q] = c->g_peer_buf[q];
-          p.peer_row_off = gather_row_off + (long long)f0 * tokens;
+          p.peer_tokens = tokens;
+          p.peer_frame_stride = gather_frame_stride;
+          p.peer_frame_off = gather_frame_off + (long long)f0 * gather_frame_stride;
         }
         TRY(launch_gemm<EPI_BIAS_RES_STATS>(c, bn_d, (bf16*)c->w_h.p, MLP, w.w2, MLP, p, st));
       }
@@ -975,12 +977,18 @@ extern "C" int vly_gather_release(vly_ctx* c, void* stream) {
 }
 
 extern "C" int vly_vit_encode_gather(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int frame_offset, int select_layer, void* stream) {
-  if (!c || F < 0 || frame_offset < 0 || (F > 0 && !pixels)) return fail(VLY_ERR_INVALID, "vly_vit_encode_gather: bad argument");
+  return vly_vit_encode_gather_strided(c, pixels, pixel_dtype, F, frame_offset, 1, select_layer, stream);
+}
+
+extern "C" int vly_vit_encode_gather_strided(vly_ctx* c, const void* pixels, int pixel_dtype, int F, int frame_offset, int frame_stride,
+                                             int select_layer, void* stream) {
+  if (!c || F < 0 || frame_offset < 0 || frame_stride < 1 || (F > 0 && !pixels)) return fail(VLY_ERR_INVALID, "vly_vit_encode_gather: bad argument");
   std::lock_guard<std::mutex> lk(c->mu);
   if (!c->finalized || !c->has_vit) return fail(VLY_ERR_STATE, "vly_vit_encode_gather: vision weights not loaded/finalised");
   if (c->g_world == 0) return fail(VLY_ERR_STATE, "vly_vit_encode_gather: call vly_gather_create / vly_gather_open_peers first");
   const int tokens = (c->cfg.vit_image / c->cfg.vit_patch) * (c->cfg.vit_image / c->cfg.vit_patch) + 1;
-  if (((long long)frame_offset + F) * tokens > c->g_rows) return fail(VLY_ERR_INVALID, "vly_vit_encode_gather: frames [%d,%d) exceed the gather buffer", frame_offset, frame_offset + F);
+  if (F > 0 && ((long long)frame_offset + (long long)(F - 1) * frame_stride + 1) * tokens > c->g_rows)
+    return fail(VLY_ERR_INVALID, "vly_vit_encode_gather: frames %d + i*%d, i < %d exceed the gather buffer", frame_offset, frame_stride, F);
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   TRY(gather_check_timeout(c, "vly_vit_encode_gather"));
@@ -992,7 +1000,7 @@ extern "C" int vly_vit_encode_gather(vly_ctx* c, const void* pixels, int pixel_d
   }
   if (F > 0) {
     TRY(ensure(c->w_xlocal, (size_t)F * tokens * c->cfg.vit_hidden * 2));       // local residual stream (scratch)
-    TRY(vit_encode_impl(c, pixels, pixel_dtype, F, select_layer, c->w_xlocal.p, stream, true, (long long)frame_offset * tokens));
+    TRY(vit_encode_impl(c, pixels, pixel_dtype, F, select_layer, c->w_xlocal.p, stream, true, frame_offset, frame_stride));
   }
   // flag exchange: every rank tells every rank "my rows are in your buffer", then waits for all of them
   const int epoch = ++c->g_epoch;

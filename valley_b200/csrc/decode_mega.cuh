@@ -65,7 +65,8 @@ struct StepParams {
   unsigned int* grid_epoch;     // launches that ran to completion; barrier k of a launch waits for (epoch * n_barriers + k) * gridDim
   int n_stages;
   int n_inflight;               // bulk copies outstanding per SM are capped at this many stages (the ring may be deeper)
-  long long* dbg;               // optional [gridDim][8] cycle counters: sync, stage-x, weight loop, attention, full-wait
+  long long* dbg;               // optional [gridDim][32] cycle counters: [0..3] sync, stage-x, weight loop, attention totals;
+                                // [8 + 3*type + {0,1,2}] = stage-x, loop, trailing grid sync of every phase of that PhaseType
 };
 
 struct MegaCfg {
@@ -212,6 +213,9 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
   // written by block 0 at the very end of the previous completed launch (stream order): the same value in every CTA
   const unsigned int sync_base = *p.grid_epoch * (unsigned int)(p.n_phases + 1) * gridDim.x;
   long long t_sync = 0, t_stage = 0, t_loop = 0, t_attn = 0, t0 = clock64();
+  long long* dbg_o = (p.dbg != nullptr && ct == 0) ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
+  if (dbg_o != nullptr)
+    for (int i = 8; i < 32; ++i) dbg_o[i] = 0;
   // ---- phase -1: x = embed[token] (decode input) ----
   {
     if (!is_fin) {
@@ -362,6 +366,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         }
       }
       t_attn += clock64() - t0;
+      if (dbg_o != nullptr) dbg_o[8 + 3 * PH_ATTN + 1] += clock64() - t0;
     } else {
       // ------------------------------ weight phase ------------------------------
       const bool norm = (d.type == PH_QKV || d.type == PH_GATEUP || d.type == PH_LOGITS);
@@ -400,6 +405,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
       }
       asm volatile("bar.sync 2, 544;" ::: "memory");
       t_stage += clock64() - t0;
+      if (dbg_o != nullptr) dbg_o[8 + 3 * d.type] += clock64() - t0;
       t0 = clock64();
       const int n_groups = (d.N + ROWS - 1) / ROWS;
       const int n_slices = (d.K + KC - 1) / KC;
@@ -558,6 +564,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         }
       }
       t_loop += clock64() - t0;
+      if (dbg_o != nullptr) dbg_o[8 + 3 * d.type + 1] += clock64() - t0;
     }
     t0 = clock64();
     if (pi == p.n_phases - 1 && is_fin && lane < p.B) {
@@ -566,10 +573,10 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
     }
     grid_sync_consumers(p.grid_counter, sync_base + (++sync_no) * gridDim.x, ct);
     t_sync += clock64() - t0;
+    if (dbg_o != nullptr) dbg_o[8 + 3 * d.type + 2] += clock64() - t0;
   }
-  if (p.dbg != nullptr && ct == 0) {
-    long long* o = p.dbg + (size_t)blockIdx.x * 8;
-    o[0] = t_sync; o[1] = t_stage; o[2] = t_loop; o[3] = t_attn; o[4] = 0;
+  if (dbg_o != nullptr) {
+    dbg_o[0] = t_sync; dbg_o[1] = t_stage; dbg_o[2] = t_loop; dbg_o[3] = t_attn; dbg_o[4] = 0;
   }
 
   // ---- greedy arg-max over the per-CTA partials (lowest index on ties, like torch.argmax); advance the counters ----

@@ -50,10 +50,13 @@ struct GemmParams {
   __nv_bfloat16* kcache;          // [B, nH, Smax, 128] for this layer
   __nv_bfloat16* vcache;
   // EPI_BIAS_RES_STATS, fused all-gather: besides `out`, every finished row is stored into the gather buffer of every
-  // rank (peer-mapped device pointers, NVLink P2P stores) at row (row + peer_row_off)
+  // rank (peer-mapped device pointers, NVLink P2P stores).  Local row m = (local frame f, token t) with f = m / peer_tokens
+  // goes to gather row ((peer_frame_off + f * peer_frame_stride) * peer_tokens + t): stride 1 = this rank owns a contiguous
+  // block of frames, stride = world size = frames dealt round-robin over the ranks
   __nv_bfloat16* peer_out[8];
   int n_peers;
-  long long peer_row_off;
+  int peer_tokens, peer_frame_stride;
+  long long peer_frame_off;
 };
 
 template <int BN>
@@ -256,6 +259,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       float st_sum = 0.f, st_sq = 0.f;
+      long long peer_row = 0;
+      if constexpr (EPI == EPI_BIAS_RES_STATS) {
+        if (p.n_peers > 0) {
+          const int f = row / p.peer_tokens;
+          peer_row = (p.peer_frame_off + (long long)f * p.peer_frame_stride) * p.peer_tokens + (row - f * p.peer_tokens);
+        }
+      }
       // one 32-column chunk: epilogue math + store
       auto process_chunk = [&](const uint32_t (&r)[32], const int c) {
         const int n0 = n_blk * BN + c * 32;
@@ -317,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int j = 0; j < 4; ++j) op[j] = o[j];
           if (p.n_peers > 0) {          // compute + collective in one kernel: the tile is pushed to every rank as it retires
             for (int q = 0; q < p.n_peers; ++q) {
-              uint4* pp = reinterpret_cast<uint4*>(p.peer_out[q] + (size_t)(row + p.peer_row_off) * p.ldo + n0);
+              uint4* pp = reinterpret_cast<uint4*>(p.peer_out[q] + (size_t)peer_row * p.ldo + n0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) pp[j] = o[j];
             }

@@ -30,12 +30,35 @@ def all_shard_sizes(n_items: int, world: int) -> List[int]:
     return [shard_bounds(n_items, world, r)[1] - shard_bounds(n_items, world, r)[0] for r in range(world)]
 
 
-def gather_frame_features(local_feats: torch.Tensor, n_frames_total: int, group=None) -> torch.Tensor:
-    """All-gather variable-size shards of frame features -> [n_frames_total, tokens, D] on every rank.
+def dealt_frames(n_items: int, world: int, rank: int) -> range:
+    """Round-robin ("interleaved") dealing: rank r owns global frames r, r + world, r + 2 world, ...  Every video's frames are
+    then spread over all ranks (balanced whatever the per-video frame counts are), so each rank NEEDS remote frames for the
+    videos it decodes -- the case the all-gather exists for (BASELINE config 4)."""
+    return range(rank, n_items, world)
+
+
+def dealt_sizes(n_items: int, world: int) -> List[int]:
+    return [len(dealt_frames(n_items, world, r)) for r in range(world)]
+
+
+def gather_frame_features(local_feats: torch.Tensor, n_frames_total: int, group=None, interleaved: bool = False) -> torch.Tensor:
+    """All-gather variable-size shards of frame features -> [n_frames_total, tokens, D] on every rank, in global frame order.
 
     Shards are padded to the largest shard so a single all_gather_into_tensor (one NCCL ncclAllGather)
-    moves everything; padding rows are dropped afterwards."""
+    moves everything; padding rows are dropped afterwards.  ``interleaved``: shards are ``dealt_frames`` instead of
+    contiguous ``shard_bounds`` blocks."""
     world = dist.get_world_size(group)
+    if interleaved:
+        sizes = dealt_sizes(n_frames_total, world)
+        mx = max(sizes)
+        assert local_feats.shape[0] == sizes[dist.get_rank(group)], (local_feats.shape, sizes)
+        if local_feats.shape[0] < mx:
+            pad = torch.zeros(mx - local_feats.shape[0], *local_feats.shape[1:], dtype=local_feats.dtype, device=local_feats.device)
+            local_feats = torch.cat([local_feats, pad], 0)
+        out = torch.empty(world * mx, *local_feats.shape[1:], dtype=local_feats.dtype, device=local_feats.device)
+        dist.all_gather_into_tensor(out, local_feats.contiguous(), group=group)
+        # out[r, i] = global frame r + i * world  ->  global order is the (i, r) transpose, minus the padding of the short shards
+        return out.view(world, mx, *local_feats.shape[1:]).transpose(0, 1).reshape(world * mx, *local_feats.shape[1:])[:n_frames_total]
     sizes = all_shard_sizes(n_frames_total, world)
     mx = max(sizes)
     assert local_feats.shape[0] == sizes[dist.get_rank(group)], (local_feats.shape, sizes)
@@ -50,11 +73,12 @@ def gather_frame_features(local_feats: torch.Tensor, n_frames_total: int, group=
 
 
 def encode_frames_sharded(encode_fn: Callable[[torch.Tensor], torch.Tensor], local_pixels: torch.Tensor,
-                          n_frames_total: int, group=None) -> torch.Tensor:
-    """rank r holds pixels of global frames shard_bounds(n_frames_total, world, r); returns ALL frame features."""
+                          n_frames_total: int, group=None, interleaved: bool = False) -> torch.Tensor:
+    """rank r holds pixels of global frames shard_bounds(n_frames_total, world, r) (or dealt_frames(...) when ``interleaved``);
+    returns ALL frame features in global frame order."""
     local = encode_fn(local_pixels) if local_pixels.shape[0] > 0 else \
         torch.zeros(0, 257, 1024, dtype=torch.bfloat16, device=local_pixels.device)
-    return gather_frame_features(local, n_frames_total, group)
+    return gather_frame_features(local, n_frames_total, group, interleaved)
 
 
 class FusedFrameGather:
@@ -83,17 +107,23 @@ class FusedFrameGather:
             __cuda_array_interface__ = {"shape": (rows, model.config.mm_hidden_size), "typestr": "<u2", "data": (buf.value, False), "version": 2}
         self.features = torch.as_tensor(_Raw(), device=model.device).view(torch.bfloat16).view(n_frames_total, self.tokens, model.config.mm_hidden_size)
 
-    def encode(self, local_pixels: torch.Tensor) -> torch.Tensor:
-        """local_pixels: frames shard_bounds(n_frames_total, world, rank) -> the [n_frames_total,257,1024] buffer (all ranks' features)."""
+    def encode(self, local_pixels: torch.Tensor, interleaved: bool = False) -> torch.Tensor:
+        """local_pixels: frames shard_bounds(n_frames_total, world, rank) -- or dealt_frames(...) when ``interleaved`` -- ->
+        the [n_frames_total,257,1024] buffer (all ranks' features, global frame order)."""
         from ._lib import check
         from .model import _DT
-        lo, hi = shard_bounds(self.n_frames_total, self.world, self.rank)
-        assert local_pixels.shape[0] == hi - lo
+        if interleaved:
+            n_local, off, stride = len(dealt_frames(self.n_frames_total, self.world, self.rank)), self.rank, self.world
+        else:
+            lo, hi = shard_bounds(self.n_frames_total, self.world, self.rank)
+            n_local, off, stride = hi - lo, lo, 1
+        assert local_pixels.shape[0] == n_local, (local_pixels.shape, n_local)
         px = local_pixels if local_pixels.dtype in _DT else local_pixels.float()
         px = px.to(self.model.device).contiguous()
-        check(self.model._lib.vly_vit_encode_gather(self.model._ctx, px.data_ptr() if hi > lo else None, _DT[px.dtype], hi - lo, lo,
-                                                    getattr(self.model.config, "mm_vision_select_layer", -1), torch.cuda.current_stream().cuda_stream))
-        return self.features
+        check(self.model._lib.vly_vit_encode_gather_strided(
+            self.model._ctx, px.data_ptr() if n_local > 0 else None, _DT[px.dtype], n_local, off, stride,
+            getattr(self.model.config, "mm_vision_select_layer", -1), torch.cuda.current_stream().cuda_stream))
+        return self.features[: self.n_frames_total]      # (the buffer may be larger than this request)
 
     def release(self):
         from ._lib import check
@@ -114,14 +144,14 @@ def my_videos(n_videos: int, group=None) -> Tuple[int, int]:
 
 
 def generate_sharded(model, input_ids: torch.Tensor, local_pixels: torch.Tensor, n_videos: int, n_frames: int,
-                     max_new_tokens: int, group=None, fused: "FusedFrameGather | None" = None) -> torch.Tensor:
-    """Config-4 style request: ``n_videos`` videos x ``n_frames`` frames, frames sharded over ranks for the ViT,
-    one all-gather, then every rank pools/projects/splices and greedy-decodes its own videos.
-    ``input_ids`` [n_videos_local, S] are this rank's prompts; returns this rank's generated ids."""
+                     max_new_tokens: int, group=None, fused: "FusedFrameGather | None" = None, interleaved: bool = False) -> torch.Tensor:
+    """Config-4 style request: ``n_videos`` videos x ``n_frames`` frames, frames sharded over ranks for the ViT
+    (contiguous blocks, or dealt round-robin when ``interleaved``), one all-gather, then every rank pools/projects/splices and
+    greedy-decodes its own videos.  ``input_ids`` [n_videos_local, S] are this rank's prompts; returns this rank's generated ids."""
     if fused is not None:
-        feats = fused.encode(local_pixels)                    # ViT + gather in one pass over NVLink
+        feats = fused.encode(local_pixels, interleaved)       # ViT + gather in one pass over NVLink
     else:
-        feats = encode_frames_sharded(model.encode_frames, local_pixels, n_videos * n_frames, group)   # plain NCCL all-gather
+        feats = encode_frames_sharded(model.encode_frames, local_pixels, n_videos * n_frames, group, interleaved)   # plain NCCL all-gather
     lo, hi = my_videos(n_videos, group)
     mine = feats.view(n_videos, n_frames, *feats.shape[1:])[lo:hi].reshape((hi - lo) * n_frames, *feats.shape[1:]).contiguous()
     B = hi - lo
