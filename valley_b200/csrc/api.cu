@@ -161,6 +161,7 @@ struct vly_kv {
   long long* cur_tokens = nullptr;    // [B]
   long long* gen_tokens = nullptr;    // [B, Smax]
   int nsplit = 1, gemv_grid = 0;
+  int stage_bytes = 0;                 // ring slot of the persistent decode kernel: max over its phases (pick_phase_geometry)
   PhaseDesc* d_phases = nullptr;
   int n_phases = 0;
   unsigned int* grid_counter = nullptr;
@@ -1142,6 +1143,57 @@ extern "C" int vly_embed_splice(vly_ctx* c, const int64_t* ids, const int32_t* s
 // ------------------------------------------------------------------------------------------------
 // KV cache
 // ------------------------------------------------------------------------------------------------
+// Shared-memory budget of the persistent decode kernel (decode_mega.cuh): activation block + barriers / handoff slots, the
+// rest is the weight ring.
+static void mega_smem_layout(const vly_config& g, int bmax, size_t* x_bytes, size_t* misc) {
+  const bool tc = bmax > 1;
+  const int kmax = g.intermediate_size > g.hidden_size ? g.intermediate_size : g.hidden_size;
+  const size_t xs_stride_b = tc ? (size_t)(((kmax * 2 + 127) & ~127) + MegaCfg::PAD_TC) : (size_t)kmax * 2;
+  *x_bytes = ((size_t)bmax * xs_stride_b + 127) & ~size_t(127);
+  const int nv = (tc ? MegaCfg::ROWS_TC : MegaCfg::ROWS) * bmax;
+  *misc = (2 * MegaCfg::MAX_STAGES + 2 * MegaCfg::RED_SLOTS + 2) * 8 + (size_t)MegaCfg::RED_SLOTS * 16 * nv * 4 + (3 + 16) * bmax * 4 + 256;
+}
+static const size_t kMegaSmem = 226 * 1024;
+
+// Ring geometry of one weight phase of the persistent decode kernel: rows per work unit and columns per stage.  Measured with
+// tools/ringbw.cu (the producer's access pattern without consumers, profiles/ringbw_r02.log):
+//   * what streams fastest is ~110-125 KB of bulk copies outstanding per SM (7.3-7.4 TB/s); 64 KB: 6.2-7.1, 190 KB: 6.7-7.0;
+//   * a bulk copy should be >= 4 KB: 8 rows x 2.5 KB stream at 5.9 TB/s where 4 rows x 5 KB reach 7.3;
+//   * the consumers need a few hundred cycles to hand a landed stage back, which takes that stage out of flight: a ring of 3
+//     large stages loses more to this than one of 5 smaller stages, so the target is a stage of 1/5 of the ring budget
+//     (but 16-48 KB), cut so that K divides into EQUAL stages (no short tail stage);
+//   * rows: the candidate (max, max / 2) that satisfies the copy-size rule, then the one whose work units balance better over
+//     the SMs -- the phase lasts as long as its most loaded CTA: N = 5120 is 5 rounds of 8 rows (40) but 9 rounds of 4 (36).
+// VLY_MEGA_STAGE_KB / VLY_MEGA_ROWS override (A/B measurements).
+static void pick_phase_geometry(int bmax, size_t ring_budget, int N, int K, int num_sms, int* rows_out, int* kc_out) {
+  const bool tc = bmax > 1;
+  const int max_rows = tc ? MegaCfg::ROWS_TC : MegaCfg::ROWS;
+  const int pad = tc ? MegaCfg::PAD_TC : 0, gran = tc ? 64 : 8;
+  static const int env_kb = getenv("VLY_MEGA_STAGE_KB") ? atoi(getenv("VLY_MEGA_STAGE_KB")) : 0;
+  static const int env_rows = getenv("VLY_MEGA_ROWS") ? atoi(getenv("VLY_MEGA_ROWS")) : 0;
+  size_t target = env_kb > 0 ? (size_t)env_kb * 1024 : ring_budget / 5;
+  if (target < 16 * 1024) target = 16 * 1024;
+  if (target > 48 * 1024) target = 48 * 1024;
+  auto kc_for = [&](int rows) {
+    const int cap = (int)((target / rows - pad) / 2);
+    const int ns = cdiv(K, cap > gran ? cap : gran);
+    int kc = cdiv(cdiv(K, ns), gran) * gran;
+    return kc > K ? cdiv(K, gran) * gran : kc;
+  };
+  int rows = max_rows;
+  if (env_rows > 0) rows = env_rows > max_rows ? max_rows : env_rows;
+  else {
+    if (kc_for(rows) * 2 < 4096 && K * 2 >= 4096) rows = max_rows / 2;            // keep every bulk copy >= 4 KB
+    if (rows == max_rows) {
+      const long long load_full = (long long)cdiv(cdiv(N, max_rows), num_sms) * max_rows;
+      const long long load_half = (long long)cdiv(cdiv(N, max_rows / 2), num_sms) * (max_rows / 2);
+      if (load_half * 100 < load_full * 97) rows = max_rows / 2;                  // at least 3 % shorter critical path
+    }
+  }
+  *rows_out = rows;
+  *kc_out = kc_for(rows);
+}
+
 extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   if (!c || !out || batch <= 0 || max_seq <= 0) return fail(VLY_ERR_INVALID, "vly_kv_create: bad argument");
   if (!c->finalized || !c->has_llm) return fail(VLY_ERR_STATE, "vly_kv_create: LLM weights not finalised");
@@ -1161,7 +1213,8 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
     int ns = (2 * c->num_sms + batch * nH - 1) / (batch * nH);
     kv->nsplit = ns < 1 ? 1 : (ns > 16 ? 16 : ns);
   } else {
-    kv->nsplit = kv->Smax / kDecSplitKeys;      // fixed 64-key splits; splits past the current length exit immediately
+    kv->nsplit = kv->Smax / MegaCfg::ATTN_KEYS; // capacity of the split dimension: the persistent kernel uses 32-key items, the
+                                                // per-op kernel fixed 64-key splits (it only touches the first Smax / 64 slots)
   }
   kv->gemv_grid = 2 * c->num_sms;
   CK(cudaMalloc((void**)&kv->d_len, 8));
@@ -1194,18 +1247,47 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   CK(cudaMemset(kv->key_bits, 0xff, (size_t)batch * kv->mask_words() * 4));
   {  // phase table of the persistent decode-step kernel: execution order of one step
     std::vector<PhaseDesc> ph;
+    const int bmax = batch <= 1 ? 1 : (batch <= 2 ? 2 : 4);
+    const int pad = bmax > 1 ? MegaCfg::PAD_TC : 0;
+    size_t x_bytes, misc;
+    mega_smem_layout(g, bmax, &x_bytes, &misc);
+    const size_t ring_budget = kMegaSmem > x_bytes + misc ? kMegaSmem - x_bytes - misc : 0;
+    kv->stage_bytes = 0;
+    auto add = [&](PhaseDesc d) {
+      d.rows = d.kc = 0;
+      if (d.type != PH_ATTN) {
+        pick_phase_geometry(bmax, ring_budget, d.N, d.K, c->num_sms, &d.rows, &d.kc);
+        const int sb = d.rows * (d.kc * 2 + pad);
+        if (sb > kv->stage_bytes) kv->stage_bytes = sb;
+      }
+      ph.push_back(d);
+    };
     for (int l = 0; l < L; ++l) {
       const LlamaLayerW& w = c->layers[l];
       PhaseDesc d = {};
       d.layer = l; d.kcache = kv->k_layer(l); d.vcache = kv->v_layer(l);
-      d.type = PH_QKV; d.N = 3 * H; d.K = H; d.W = w.wqkv; d.x_in = kv->x; d.out = kv->q; ph.push_back(d);
-      d.type = PH_ATTN; d.N = 0; d.K = 0; d.W = nullptr; d.x_in = nullptr; d.out = kv->attn; ph.push_back(d);
-      d.type = PH_OPROJ; d.N = H; d.K = H; d.W = w.wo; d.x_in = kv->attn; d.out = kv->x; ph.push_back(d);
-      d.type = PH_GATEUP; d.N = 2 * I; d.K = H; d.W = w.wgu; d.x_in = kv->x; d.out = kv->hb; ph.push_back(d);
-      d.type = PH_DOWN; d.N = H; d.K = I; d.W = w.wdown; d.x_in = kv->hb; d.out = kv->x; ph.push_back(d);
+      d.type = PH_QKV; d.N = 3 * H; d.K = H; d.W = w.wqkv; d.x_in = kv->x; d.out = kv->q; add(d);
+      d.type = PH_ATTN; d.N = 0; d.K = 0; d.W = nullptr; d.x_in = nullptr; d.out = kv->attn; add(d);
+      d.type = PH_OPROJ; d.N = H; d.K = H; d.W = w.wo; d.x_in = kv->attn; d.out = kv->x; add(d);
+      d.type = PH_GATEUP; d.N = 2 * I; d.K = H; d.W = w.wgu; d.x_in = kv->x; d.out = kv->hb; add(d);
+      d.type = PH_DOWN; d.N = H; d.K = I; d.W = w.wdown; d.x_in = kv->hb; d.out = kv->x; add(d);
     }
     PhaseDesc d = {};
-    d.type = PH_LOGITS; d.N = V; d.K = H; d.W = c->lm_head; d.x_in = kv->x; d.out = nullptr; ph.push_back(d);
+    d.type = PH_LOGITS; d.N = V; d.K = H; d.W = c->lm_head; d.x_in = kv->x; d.out = nullptr; add(d);
+    kv->stage_bytes = (kv->stage_bytes + 127) & ~127;
+    for (PhaseDesc& q : ph) {          // stages of this phase's size that make ~116 KB of copies outstanding per SM
+      if (q.type == PH_ATTN) continue;
+      const int sb = q.rows * (q.kc * 2 + pad);
+      q.inflight = (116 * 1024 + sb / 2) / sb;
+      if (q.inflight < 2) q.inflight = 2;
+    }
+    if (getenv("VLY_MEGA_DBG")) {
+      const int n_fit = (int)(ring_budget / kv->stage_bytes);
+      fprintf(stderr, "[vly] decode ring: B=%d x=%zu B, ring budget %zu B, slot %d B, %d slots fit;", batch, x_bytes, ring_budget, kv->stage_bytes, n_fit);
+      for (int i = 0; i < 5 && i < (int)ph.size(); ++i)
+        if (ph[i].type != PH_ATTN) fprintf(stderr, " type%d N=%d K=%d rows=%d kc=%d inflight=%d;", ph[i].type, ph[i].N, ph[i].K, ph[i].rows, ph[i].kc, ph[i].inflight);
+      fprintf(stderr, " logits rows=%d kc=%d\n", ph.back().rows, ph.back().kc);
+    }
     kv->n_phases = (int)ph.size();
     CK(cudaMalloc((void**)&kv->d_phases, ph.size() * sizeof(PhaseDesc)));
     CK(cudaMemcpy(kv->d_phases, ph.data(), ph.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice));
@@ -1388,7 +1470,8 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
     }
     {
       DecAttnParams p = {};
-      p.B = nb; p.nH = nH; p.H = H; p.Smax = kv->Smax; p.nsplit = kv->nsplit; p.seq_len = kv->d_len;
+      p.B = nb; p.nH = nH; p.H = H; p.Smax = kv->Smax; p.seq_len = kv->d_len;
+      p.nsplit = use_decode_v1() ? kv->nsplit : kv->Smax / kDecSplitKeys;
       p.q = q; p.kcache = kc; p.vcache = vc;
       p.part_o = kv->part_o + (size_t)b0 * nH * kv->nsplit * 128;
       p.part_ml = kv->part_ml + (size_t)b0 * nH * kv->nsplit;
@@ -1402,7 +1485,7 @@ static int enqueue_decode_step(vly_ctx* c, vly_kv* kv, int b0, int nb, bool bump
         CKL();
       } else {
         TRY(ensure_smem_attr(c->cfg.device, decode_attention_v2_kernel, 0, true));
-        dim3 grid(nb * nH, kv->nsplit);
+        dim3 grid(nb * nH, p.nsplit);
         CK(launch_ex(decode_attention_v2_kernel, grid, dim3(128), 0, st, true, p));
       }
       c->launches++;
@@ -1582,28 +1665,22 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
     p.dbg = want ? kv->dbg : nullptr;
     g_mega_dbg = kv->dbg;
   }
-  const bool tc = bmax > 1;                                    // tensor-core consumers use padded strides (decode_mega.cuh)
-  const size_t xs_stride_b = tc ? (size_t)(((p.Kmax * 2 + 127) & ~127) + 64) : (size_t)p.Kmax * 2;
-  size_t x_bytes = ((size_t)bmax * xs_stride_b + 127) & ~size_t(127);
-  if (x_bytes < (size_t)MegaCfg::ATTN_SCRATCH) x_bytes = MegaCfg::ATTN_SCRATCH;      // the attention scratch aliases the x block
-  const size_t stage_b = tc ? MegaCfg::STAGE_BYTES_TC : MegaCfg::STAGE_BYTES;
-  const size_t misc = (2 * MegaCfg::MAX_STAGES + 2 * MegaCfg::RED_SLOTS) * 8 + MegaCfg::RED_SLOTS * 16 * 8 * bmax * 4 + 128 * bmax + 512;
-  int n_stages = (int)((226 * 1024 - (long long)x_bytes - (long long)misc) / (long long)stage_b);
+  size_t x_bytes, misc;
+  mega_smem_layout(g, bmax, &x_bytes, &misc);
+  const size_t stage_b = (size_t)kv->stage_bytes;
+  int n_stages = (int)(((long long)kMegaSmem - (long long)x_bytes - (long long)misc) / (long long)stage_b);
   if (n_stages > MegaCfg::MAX_STAGES) n_stages = MegaCfg::MAX_STAGES;
   {
-    // measured on B200 (tools/membw.cu): ~96 KB of bulk copies in flight per SM streams at 7.2-7.5 TB/s, 192 KB at 5.2-6 TB/s
-    // A deeper ring with the copies in flight still capped at 3 stages (VLY_MEGA_STAGES=6 VLY_MEGA_INFLIGHT=3) was measured too:
-    // the weight loop shrinks by 0.16 ms/step (the extra slots fill during barriers and the attention phase) but the grid
-    // barriers grow by the same amount -- the critical path is the 48 CTAs that own attention items, not HBM -- so 3 stays.
-    static const int want = getenv("VLY_MEGA_STAGES") ? atoi(getenv("VLY_MEGA_STAGES")) : 3;
-    if (n_stages > want) n_stages = want;
-  }
-  {
-    static const int inflight = getenv("VLY_MEGA_INFLIGHT") ? atoi(getenv("VLY_MEGA_INFLIGHT")) : 3;
-    p.n_inflight = inflight < 1 ? 1 : (inflight > n_stages ? n_stages : inflight);
+    // depth of the ring and number of stages kept in flight: see pick_phase_geometry.  VLY_MEGA_STAGES / VLY_MEGA_INFLIGHT override.
+    static const int want = getenv("VLY_MEGA_STAGES") ? atoi(getenv("VLY_MEGA_STAGES")) : 0;
+    if (want > 0 && n_stages > want) n_stages = want;
+    static const int inflight = getenv("VLY_MEGA_INFLIGHT") ? atoi(getenv("VLY_MEGA_INFLIGHT")) : 0;
+    p.n_inflight = inflight > 0 ? inflight : n_stages;                        // (PhaseDesc::inflight is the per-phase value)
+    if (p.n_inflight > n_stages) p.n_inflight = n_stages;
   }
   if (n_stages < 2) return fail(VLY_ERR_INVALID, "decode: activations (B=%d, K=%d) leave no room for the weight ring", B, p.Kmax);
   p.n_stages = n_stages;
+  p.stage_bytes = (int)stage_b;
   const size_t smem = (size_t)n_stages * stage_b + x_bytes + misc;
   void* args[] = {&p};
   cudaError_t e;

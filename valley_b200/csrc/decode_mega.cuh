@@ -1,21 +1,25 @@
 // One persistent cooperative kernel per decode step ("mega-kernel").
 //
-// Decode at B <= 4 is pure weight streaming (13.2 GB / step at 7B).  Launching 5 kernels per layer leaves the HBM idle
-// at every kernel boundary (launch gap, activation staging, first-load latency, tail imbalance: ~5 us x 160 per step).
+// Decode at B <= 4 is pure weight streaming (13.2 GB / step at 7B, 25.7 GB at 13B).  Launching 5 kernels per layer leaves the
+// HBM idle at every kernel boundary (launch gap, activation staging, first-load latency, tail imbalance: ~5 us x 160 per step).
 // Here ONE kernel runs the whole step on one CTA per SM:
 //   warp 0 (1 thread) : producer -- walks the step's weight matrices in execution order (QKV, o_proj, gate/up, down of
 //                       every layer, then lm_head) and streams this CTA's rows through a shared-memory ring with 1-D bulk
-//                       (TMA) copies: 4 rows x 4096 columns = 32 KB per stage, mbarrier complete_tx.  It never waits for a
-//                       phase boundary -- weights do not depend on activations -- so while the consumers sit in a grid
-//                       barrier the ring fills with the NEXT phase's weights and HBM keeps streaming.
-//   warps 1..16       : compute -- per phase: stage the activation rows in shared memory (RMSNorm statistics where a
-//                       norm is folded), multiply the ring stages (fp32 accumulate), warp-reduce, and hand the 16 per-warp
-//                       partials of a 4-row unit to the finalize warp through a 4-slot mbarrier handoff -- there is NO
-//                       blocking barrier inside the streaming loop.  The attention phase runs on four 128-thread teams
-//                       (split-KV, last-arriver merge).  Phases are separated by a grid-wide barrier.
+//                       (TMA) copies, mbarrier complete_tx.  It never waits for a phase boundary -- weights do not depend on
+//                       activations -- so while the consumers sit in a grid barrier the ring fills with the NEXT phase's
+//                       weights and HBM keeps streaming.  The ring geometry is PER PHASE (PhaseDesc::rows, ::kc, chosen on the
+//                       host per matrix shape): K is cut into equal stages (no short tail stage: 5120 = 2 x 2560, not
+//                       2048 + 2048 + 1024) and the rows per work unit are picked so the units balance over the 148 SMs
+//                       (5120 rows = 640 units of 8 = 4.3 per SM -> 5 rounds at 86 %; 1280 units of 4 -> 9 rounds at 96 %).
+//   warps 1..16       : compute -- per phase: the activation rows arrive in shared memory by bulk copy (RMSNorm statistics
+//                       where a norm is folded), multiply the ring stages (fp32 accumulate), warp-reduce, and hand the 16
+//                       per-warp partials of a work unit to the finalize warp through a 4-slot mbarrier handoff -- there is NO
+//                       blocking barrier inside the streaming loop.  The attention phase runs warp-per-item (32 keys of one
+//                       (sequence, head) per item, online softmax in registers, last-arriver merge): no block-level barrier.
+//                       Phases are separated by a grid-wide barrier.
 //   warp 17           : finalize -- sums the partials and runs the fused epilogue (RoPE + KV append, SwiGLU, residual,
 //                       logits + running arg-max); its global operands are prefetched while the unit is being computed.
-// Cross-CTA activations are read with ld.global.cg (L2) -- the L1 of an SM is not coherent with other SMs' writes.
+// Cross-CTA activations are read through L2 (bulk copies / ld.global.cg) -- the L1 of an SM is not coherent with other SMs' writes.
 #pragma once
 #include "common.cuh"
 #include "simt_kernels.cuh"
@@ -28,6 +32,9 @@ enum PhaseType : int { PH_QKV = 0, PH_ATTN = 1, PH_OPROJ = 2, PH_GATEUP = 3, PH_
 
 struct PhaseDesc {
   int type, N, K, layer;
+  int rows, kc;                 // ring geometry of this phase: weight rows per work unit, columns per ring stage
+  int inflight;                 // stages of THIS phase's size kept in flight (~116 KB of bulk copies outstanding per SM)
+  int pad_;
   const __nv_bfloat16* W;       // [N, K] (nullptr for PH_ATTN)
   const __nv_bfloat16* x_in;    // activation rows [B, K]
   __nv_bfloat16* out;           // QKV: q [B,H]; OPROJ/DOWN: x [B,H] (in place, also the residual); GATEUP: hb [B,I]
@@ -51,7 +58,7 @@ struct StepParams {
   float* part_o;                // [B*nH, nsplit, 128]
   float2* part_ml;              // [B*nH, nsplit]
   unsigned int* attn_counters;  // [B*nH]
-  int nsplit;
+  int nsplit;                   // capacity of the split dimension (Smax / ATTN_KEYS)
   const uint32_t* key_bits;     // [B, mask_words] attention_mask, one bit per cache position (1 = attend)
   int mask_words;
   float* logits;                // [B, V]
@@ -64,23 +71,22 @@ struct StepParams {
   unsigned int* grid_counter;   // monotonically increasing arrival counter of the grid barrier (never reset: no memset node per step)
   unsigned int* grid_epoch;     // launches that ran to completion; barrier k of a launch waits for (epoch * n_barriers + k) * gridDim
   int n_stages;
-  int n_inflight;               // bulk copies outstanding per SM are capped at this many stages (the ring may be deeper)
+  int stage_bytes;              // ring slot size: max over the phases of rows * (kc * 2 + row pad)
+  int n_inflight;               // global cap on the stages in flight (PhaseDesc::inflight is the per-phase value; the ring may be deeper)
   long long* dbg;               // optional [gridDim][32] cycle counters: [0..3] sync, stage-x, weight loop, attention totals;
                                 // [8 + 3*type + {0,1,2}] = stage-x, loop, trailing grid sync of every phase of that PhaseType
 };
 
 struct MegaCfg {
-  static constexpr int ROWS = 4, KC = 4096;
-  static constexpr int STAGE_BYTES = ROWS * KC * 2;   // 32 KB
-  // BMAX > 1 (tensor-core consumers): a stage is 8 weight rows x 2048 columns; rows of a stage / of the activation block are
-  // 64 bytes apart modulo 128, so the 16-byte fragment loads of a quarter-warp never share a bank
-  static constexpr int ROWS_TC = 8, KC_TC = 2048;
-  static constexpr int ROW_STRIDE_TC = KC_TC * 2 + 64;
-  static constexpr int STAGE_BYTES_TC = ROWS_TC * ROW_STRIDE_TC;
+  static constexpr int ROWS = 4;                         // CUDA-core path (B = 1): at most 4 weight rows per work unit
+  static constexpr int ROWS_TC = 8;                      // tensor-core path (B = 2..4): at most 8 (the N of an m16n8k16 MMA)
+  static constexpr int PAD_TC = 64;                      // tensor-core path: rows of a ring stage / of the activation block are
+                                                         // 64 bytes apart modulo 128, so the 16-byte fragment loads of a
+                                                         // quarter-warp never share a bank
   static constexpr int CONSUMERS = 512, THREADS = 576;   // producer warp + 16 compute warps + 1 finalize warp
   static constexpr int RED_SLOTS = 4;
-  static constexpr int MAX_STAGES = 6;
-  static constexpr int ATTN_SCRATCH = 4 * (64 + 8 * 128 + 8) * 4;   // per team: scores[64] + redg[8][128] + wr
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int ATTN_KEYS = 32;                   // keys per attention work item (one warp, two passes of 16)
 };
 
 VLY_DEVINL uint4 ldcg_v4(const void* p) {
@@ -105,6 +111,8 @@ VLY_DEVINL uint32_t ld_acquire_u32(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// generic-proxy writes (other CTAs', made visible by the grid barrier) -> async-proxy (bulk copy) reads of global memory
+VLY_DEVINL void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
 
 // consumers-only grid barrier (512 threads per CTA take part; the producer warp streams on)
 VLY_DEVINL void grid_sync_consumers(unsigned int* counter, unsigned int target, int ct) {
@@ -121,33 +129,27 @@ template <int BMAX>
 __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p) {
   using M = MegaCfg;
   constexpr bool kTC = BMAX > 1;                                                         // tensor-core consumers
-  constexpr int ROWS = kTC ? M::ROWS_TC : M::ROWS;                                       // weight rows per work unit
-  constexpr int KC = kTC ? M::KC_TC : M::KC;                                             // columns per ring stage
+  constexpr int ROWS = kTC ? M::ROWS_TC : M::ROWS;                                       // max weight rows per work unit
   constexpr int NV = ROWS * BMAX;
-  constexpr int ROW_STRIDE = kTC ? M::ROW_STRIDE_TC : M::KC * 2;                         // bytes between rows of a ring stage
-  constexpr int STAGE_B = kTC ? M::STAGE_BYTES_TC : M::STAGE_BYTES;
+  constexpr int PAD = kTC ? M::PAD_TC : 0;                                               // bytes appended to every ring / activation row
   extern __shared__ uint8_t msm_raw[];
   uint8_t* msm = msm_raw + ((128u - (smem_u32(msm_raw) & 127u)) & 127u);
-  uint8_t* ring = msm;                                                                   // [n_stages][4][ROW_STRIDE]
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ring + (size_t)p.n_stages * STAGE_B);   // [BMAX][xs_stride]
+  uint8_t* ring = msm;                                                                   // [n_stages][stage_bytes]
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ring + (size_t)p.n_stages * p.stage_bytes);   // [BMAX][xs_stride]
   // activation rows: stride == Kmax for the CUDA-core path; == 64 bytes modulo 128 for the tensor-core path
-  const int xs_stride = kTC ? (((p.Kmax * 2 + 127) & ~127) + 64) / 2 : p.Kmax;
-  // the attention teams' scratch ALIASES the activation block: x is re-staged at the start of every weight phase and is
-  // dead during the attention phase (this keeps a third ring stage at 13B, B = 4 where x alone is 110 KB)
-  size_t xs_bytes = ((size_t)BMAX * xs_stride * 2 + 127) & ~size_t(127);
-  if (xs_bytes < (size_t)M::ATTN_SCRATCH) xs_bytes = M::ATTN_SCRATCH;
+  const int xs_stride = kTC ? (((p.Kmax * 2 + 127) & ~127) + PAD) / 2 : p.Kmax;
+  const size_t xs_bytes = ((size_t)BMAX * xs_stride * 2 + 127) & ~size_t(127);
   uint8_t* tail = reinterpret_cast<uint8_t*>(xs) + xs_bytes;
-  float* scratch = reinterpret_cast<float*>(xs);                                         // attention teams
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + M::MAX_STAGES;
   uint64_t* red_full = empty_bar + M::MAX_STAGES;                                        // [RED_SLOTS]
   uint64_t* red_empty = red_full + M::RED_SLOTS;                                         // [RED_SLOTS]
-  float* red = reinterpret_cast<float*>(red_empty + M::RED_SLOTS);                       // [RED_SLOTS][16][NV]
+  uint64_t* x_bar = red_empty + M::RED_SLOTS;                                            // activation block landed
+  float* red = reinterpret_cast<float*>(x_bar + 2);                                      // [RED_SLOTS][16][NV]
   float* rstd_s = red + M::RED_SLOTS * 16 * NV;                                          // [BMAX]
   float* bestv = rstd_s + BMAX;                                                          // [BMAX]
   int* besti = reinterpret_cast<int*>(bestv + BMAX);                                     // [BMAX]
   float* wred = reinterpret_cast<float*>(besti + BMAX);                                  // [16][BMAX]
-  int* team_flag = reinterpret_cast<int*>(wred + 16 * BMAX);                             // [4]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (p.sample->all_done) return;       // every sequence has produced its stop token: the remaining replays are no-ops
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
       mbar_init(&red_full[i], 16);
       mbar_init(&red_empty[i], 1);
     }
+    mbar_init(x_bar, 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -169,30 +172,39 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      // The ring is deeper than the number of copies kept in flight: ~96 KB outstanding per SM is what streams fastest
-      // (tools/membw.cu), but while the consumers sit in a grid barrier / stage activations the extra slots keep HBM busy.
-      int wst = 0, issued = 0;
+      // The ring may be deeper than the number of copies kept in flight: what streams fastest is a bounded number of bytes
+      // outstanding per SM (tools/ringbw.cu), but while the consumers sit in a grid barrier / stage activations the extra
+      // slots keep HBM busy.
+      int wst = 0, issued = 0, confirmed = 0;
       uint32_t wph = 0;
       for (int pi = 0; pi < p.n_phases; ++pi) {
         const PhaseDesc& d = p.phases[pi];
         if (d.type == PH_ATTN) continue;
-        const int n_groups = (d.N + ROWS - 1) / ROWS;
-        const int n_slices = (d.K + KC - 1) / KC;
+        const int rows_u = d.rows, KCp = d.kc;
+        const int row_stride = KCp * 2 + PAD;
+        const int n_groups = (d.N + rows_u - 1) / rows_u;
+        const int n_slices = (d.K + KCp - 1) / KCp;
+        const int infl = min(d.inflight, p.n_inflight);
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-          const int n0 = g * ROWS;
-          const int rows = min(ROWS, d.N - n0);
+          const int n0 = g * rows_u;
+          const int rows = min(rows_u, d.N - n0);
           for (int s = 0; s < n_slices; ++s) {
-            const int kc = min(KC, d.K - s * KC);
+            const int kc = min(KCp, d.K - s * KCp);
             mbar_wait(&empty_bar[st], ph ^ 1);
-            if (issued >= p.n_inflight) {                 // copy #(issued - n_inflight) must have landed
+            while (issued - confirmed >= infl) {          // at most `infl` copies outstanding: the oldest must have landed
               mbar_wait(&full_bar[wst], wph);
               if (++wst == p.n_stages) { wst = 0; wph ^= 1; }
+              ++confirmed;
             }
             ++issued;
             mbar_expect_tx(&full_bar[st], (uint32_t)rows * kc * 2);
-            uint8_t* dst = ring + (size_t)st * STAGE_B;
-            const __nv_bfloat16* src = d.W + (size_t)n0 * d.K + (size_t)s * KC;
-            for (int r = 0; r < rows; ++r) bulk_load_1d(dst + r * ROW_STRIDE, src + (size_t)r * d.K, (uint32_t)kc * 2, &full_bar[st]);
+            uint8_t* dst = ring + (size_t)st * p.stage_bytes;
+            const __nv_bfloat16* src = d.W + (size_t)n0 * d.K + (size_t)s * KCp;
+            if (PAD == 0 && kc == d.K) {                  // whole rows, unpadded: the unit is ONE contiguous block
+              bulk_load_1d(dst, src, (uint32_t)rows * kc * 2, &full_bar[st]);
+            } else {
+              for (int r = 0; r < rows; ++r) bulk_load_1d(dst + r * row_stride, src + (size_t)r * d.K, (uint32_t)kc * 2, &full_bar[st]);
+            }
             if (++st == p.n_stages) { st = 0; ph ^= 1; }
           }
         }
@@ -235,134 +247,159 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
   }
 
   int st = 0;
-  uint32_t ph = 0;
+  uint32_t ph = 0, xph = 0;
   unsigned int unit_no = 0;           // running work-unit counter of this CTA: selects the handoff slot
   for (int pi = 0; pi < p.n_phases; ++pi) {
     const PhaseDesc d = p.phases[pi];
     t0 = clock64();
     if (d.type == PH_ATTN) {
       if (!is_fin) {
-        // ------------------------------ attention: 4 teams of 128 threads ------------------------------
-        const int tm = cw >> 2, tt = ct & 127, tw = cw & 3;
-        float* sc = scratch + tm * (64 + 8 * 128 + 8);
-        float* redg = sc + 64;
+        // ------------------------------ attention: one warp per (sequence, head, 32-key split) ------------------------------
+        // A half-warp covers one key row (16 lanes x 16 bytes = 128 head dims); a pass handles 16 keys (8 per half-warp): all 8 K
+        // and 8 V rows of a lane are requested up front (one L2 / HBM round trip), scores are reduced with a transposing shuffle
+        // tree (8 instead of 32 shuffles), softmax runs online in registers across the two passes of an item, P.V accumulates per
+        // lane over its 8 head dims.  Items are dealt warp-major over the SMs so one layer's K/V is pulled by every SM at once.
         const int len = pos + 1;
-        const int n_act = (len + 63) >> 6;
+        const int n_act = (len + M::ATTN_KEYS - 1) / M::ATTN_KEYS;
         const int items = p.B * p.nH * n_act;
-        const int hl = lane & 15;
-        // items are dealt team-major: every CTA's team 0 first, so the K/V rows of one layer are requested by as many SMs as
-        // possible (an SM pulls ~50-100 GB/s; four 32 KB items on one SM were the critical path of the phase)
-        for (int it = tm * gridDim.x + blockIdx.x; it < items; it += gridDim.x * 4) {
+        const int hl = lane & 15, hw = lane >> 4;
+        for (int it = cw * gridDim.x + blockIdx.x; it < items; it += gridDim.x * 16) {
           const int split = it % n_act, bh = it / n_act;
-          const int b = bh / p.nH, h = bh % p.nH;
-          const int k0 = split * 64, nk = min(len, k0 + 64) - k0;
-          const __nv_bfloat16* kb = d.kcache + ((size_t)bh * p.Smax) * 128;
-          const __nv_bfloat16* vb = d.vcache + ((size_t)bh * p.Smax) * 128;
+          const int b = bh / p.nH, h = bh - b * p.nH;
+          const int k0 = split * M::ATTN_KEYS, nk = min(len - k0, M::ATTN_KEYS);
+          const __nv_bfloat16* kb = d.kcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
+          const __nv_bfloat16* vb = d.vcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
+          const uint32_t kbits = __ldg(p.key_bits + (size_t)b * p.mask_words + split);     // one mask word per 32 keys
           float qf[8];
           {
             const uint4 w = ldcg_v4(p.q + (size_t)b * p.H + h * 128 + hl * 8);
             qf[0] = bf16_lo(w.x); qf[1] = bf16_hi(w.x); qf[2] = bf16_lo(w.y); qf[3] = bf16_hi(w.y);
             qf[4] = bf16_lo(w.z); qf[5] = bf16_hi(w.z); qf[6] = bf16_lo(w.w); qf[7] = bf16_hi(w.w);
           }
-          // every K and V row this thread needs is requested up front (one L2 round trip instead of 16 serialised ones):
-          // scores: half-warp per key, keys tw*2 + (lane>>4) + 8j;  P.V: 16 threads per key, keys (tt>>4) + 8j
-          uint4 kw[8], vw[8];
-          const int ki0 = tw * 2 + (lane >> 4), vi0 = tt >> 4, dl = tt & 15;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int ik = ki0 + 8 * j, iv = vi0 + 8 * j;
-            kw[j] = (ik < nk) ? ldcg_v4(kb + (size_t)(k0 + ik) * 128 + hl * 8) : make_uint4(0, 0, 0, 0);
-            vw[j] = (iv < nk) ? ldcg_v4(vb + (size_t)(k0 + iv) * 128 + dl * 8) : make_uint4(0, 0, 0, 0);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int i = ki0 + 8 * j;
-            const uint4 w = kw[j];
-            float dd = qf[0] * bf16_lo(w.x) + qf[1] * bf16_hi(w.x) + qf[2] * bf16_lo(w.y) + qf[3] * bf16_hi(w.y) +
-                       qf[4] * bf16_lo(w.z) + qf[5] * bf16_hi(w.z) + qf[6] * bf16_lo(w.w) + qf[7] * bf16_hi(w.w);
-            dd += __shfl_xor_sync(0xffffffffu, dd, 8);
-            dd += __shfl_xor_sync(0xffffffffu, dd, 4);
-            dd += __shfl_xor_sync(0xffffffffu, dd, 2);
-            dd += __shfl_xor_sync(0xffffffffu, dd, 1);
-            if (i < nk && hl == 0) sc[i] = dd * p.scale_log2e;
-          }
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-          // attention_mask: one bit per cache position, two words per 64-key split (all ones unless the caller masked keys)
-          const uint2 kbits = __ldg(reinterpret_cast<const uint2*>(p.key_bits + (size_t)b * p.mask_words + (k0 >> 5)));
-          const float s0 = (lane < nk && ((kbits.x >> lane) & 1u)) ? sc[lane] : -INFINITY;
-          const float s1 = (lane + 32 < nk && ((kbits.y >> lane) & 1u)) ? sc[lane + 32] : -INFINITY;
-          const float mx = warp_max(fmaxf(s0, s1));
-          const float e0 = s0 > -INFINITY ? fast_exp2(s0 - mx) : 0.f, e1 = s1 > -INFINITY ? fast_exp2(s1 - mx) : 0.f;
-          const float l = warp_sum(e0 + e1);
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-          if (tw == 0) {
-            if (lane < nk) sc[lane] = e0;
-            if (lane + 32 < nk) sc[lane + 32] = e1;
-          }
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-          {
-            const int g = vi0;
-            float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          float m_run = -INFINITY, l_run = 0.f;
+          float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int kk0 = 0; kk0 < nk; kk0 += 16) {
+            uint4 kw[8], vw[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int i = g + 8 * j;
-              const float pw = (i < nk) ? sc[i] : 0.f;
+              const int key = kk0 + 2 * j + hw;
+              const bool ok = key < nk;
+              kw[j] = ok ? ldcg_v4(kb + (size_t)key * 128) : make_uint4(0, 0, 0, 0);
+              vw[j] = ok ? ldcg_v4(vb + (size_t)key * 128) : make_uint4(0, 0, 0, 0);
+            }
+            float sc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 w = kw[j];
+              sc[j] = qf[0] * bf16_lo(w.x) + qf[1] * bf16_hi(w.x) + qf[2] * bf16_lo(w.y) + qf[3] * bf16_hi(w.y) +
+                      qf[4] * bf16_lo(w.z) + qf[5] * bf16_hi(w.z) + qf[6] * bf16_lo(w.w) + qf[7] * bf16_hi(w.w);
+            }
+            // transposing reduction over the 16 lanes of the half-warp: afterwards sc[0] = the full dot product of key
+            // kk0 + 2 * (hl >> 1) + hw (held twice: lanes hl and hl ^ 1)
+#pragma unroll
+            for (int off = 8, n = 4; off >= 2; off >>= 1, n >>= 1) {
+              const bool up = (hl & off) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (i < n) {
+                  const float send = up ? sc[i] : sc[i + n];
+                  const float keep = up ? sc[i + n] : sc[i];
+                  sc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+            }
+            sc[0] += __shfl_xor_sync(0xffffffffu, sc[0], 1);
+            const int my_key = kk0 + 2 * (hl >> 1) + hw;
+            const bool valid = my_key < nk && ((kbits >> my_key) & 1u);
+            const float s_my = valid ? sc[0] * p.scale_log2e : -INFINITY;
+            float mx = s_my;
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+            const float m_new = fmaxf(m_run, mx);
+            const float pm = valid ? fast_exp2(s_my - m_new) : 0.f;              // (valid => m_new is finite)
+            const float corr = (m_run > -INFINITY) ? fast_exp2(m_run - m_new) : 0.f;
+            float ls = pm;                                                         // every key is held by a lane pair: skip xor 1
+            ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+            ls += __shfl_xor_sync(0xffffffffu, ls, 4);
+            ls += __shfl_xor_sync(0xffffffffu, ls, 8);
+            ls += __shfl_xor_sync(0xffffffffu, ls, 16);
+            l_run = l_run * corr + ls;
+            m_run = m_new;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] *= corr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float pj = __shfl_sync(0xffffffffu, pm, (lane & 16) + 2 * j);  // weight of key kk0 + 2j + hw
               const uint4 w = vw[j];
-              o[0] = fmaf(pw, bf16_lo(w.x), o[0]); o[1] = fmaf(pw, bf16_hi(w.x), o[1]);
-              o[2] = fmaf(pw, bf16_lo(w.y), o[2]); o[3] = fmaf(pw, bf16_hi(w.y), o[3]);
-              o[4] = fmaf(pw, bf16_lo(w.z), o[4]); o[5] = fmaf(pw, bf16_hi(w.z), o[5]);
-              o[6] = fmaf(pw, bf16_lo(w.w), o[6]); o[7] = fmaf(pw, bf16_hi(w.w), o[7]);
+              o[0] = fmaf(pj, bf16_lo(w.x), o[0]); o[1] = fmaf(pj, bf16_hi(w.x), o[1]);
+              o[2] = fmaf(pj, bf16_lo(w.y), o[2]); o[3] = fmaf(pj, bf16_hi(w.y), o[3]);
+              o[4] = fmaf(pj, bf16_lo(w.z), o[4]); o[5] = fmaf(pj, bf16_hi(w.z), o[5]);
+              o[6] = fmaf(pj, bf16_lo(w.w), o[6]); o[7] = fmaf(pj, bf16_hi(w.w), o[7]);
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) redg[g * 128 + dl * 8 + e] = o[e];
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-          float ot = 0.f;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) ot += redg[g * 128 + tt];
-          p.part_o[((size_t)bh * p.nsplit + split) * 128 + tt] = ot;
-          if (tt == 0) p.part_ml[(size_t)bh * p.nsplit + split] = make_float2(mx, l);
+          for (int e = 0; e < 8; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);   // even + odd keys
+          if (n_act == 1) {
+            // the whole (sequence, head) fitted one item: no partials, no merge
+            if (hw == 0) {
+              const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+              *reinterpret_cast<uint4*>(p.attn + (size_t)b * p.H + h * 128 + hl * 8) =
+                  make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
+                             pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
+            }
+            continue;
+          }
+          float* po = p.part_o + ((size_t)bh * p.nsplit + split) * 128 + hl * 8;
+          if (hw == 0) {
+            *reinterpret_cast<float4*>(po) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(po + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          if (lane == 0) p.part_ml[(size_t)bh * p.nsplit + split] = make_float2(m_run, l_run);
           __threadfence();
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-          if (tt == 0) team_flag[tm] = (atomicAdd(p.attn_counters + bh, 1u) == (unsigned)n_act - 1);
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");
-          if (team_flag[tm]) {
+          __syncwarp();
+          int last = 0;
+          if (lane == 0) last = (atomicAdd(p.attn_counters + bh, 1u) == (unsigned)n_act - 1);
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {
+            // ---- merge of the n_act (<= 64) partials by the warp that arrived last: lane s holds (max, sum) of splits s, s + 32 ----
             __threadfence();
-            float L = 0.f, acc = 0.f;
-            if (n_act <= 32) {
-              // the merge sits on the critical path of the phase: one L2 round trip for the (max, sum) pairs -- lane s holds
-              // split s -- and batches of eight independent loads for the partial outputs, instead of 2 n_act dependent ones
-              float ms = -INFINITY, ls = 0.f;
-              if (lane < n_act) {
-                const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane]);
-                ms = ml.x;
-                ls = ml.y;
-              }
-              const float Mx = warp_max(ms);
-              const float wgt = ls > 0.f ? fast_exp2(ms - Mx) : 0.f;          // a fully masked split has m = -inf, l = 0
-              L = warp_sum(ls * wgt);
-              for (int s0 = 0; s0 < n_act; s0 += 8) {
-                float v[8];
+            float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
+            if (lane < n_act) {
+              const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane]);
+              m0 = ml.x; l0 = ml.y;
+            }
+            if (lane + 32 < n_act) {
+              const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane + 32]);
+              m1 = ml.x; l1 = ml.y;
+            }
+            const float Mx = warp_max(fmaxf(m0, m1));
+            const float w0 = l0 > 0.f ? fast_exp2(m0 - Mx) : 0.f;                 // a fully masked split has m = -inf, l = 0
+            const float w1 = l1 > 0.f ? fast_exp2(m1 - Mx) : 0.f;
+            const float L = warp_sum(l0 * w0 + l1 * w1);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* pb = p.part_o + (size_t)bh * p.nsplit * 128 + lane * 4;
+            for (int s0 = 0; s0 < n_act; s0 += 8) {
+              float4 v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  v[j] = (s0 + j < n_act) ? __ldcg(p.part_o + ((size_t)bh * p.nsplit + s0 + j) * 128 + tt) : 0.f;
+              for (int j = 0; j < 8; ++j)
+                v[j] = (s0 + j < n_act) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)(s0 + j) * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc = fmaf(v[j], __shfl_sync(0xffffffffu, wgt, (s0 + j) & 31), acc);
-              }
-            } else {
-              float Mx = -INFINITY;
-              for (int s = 0; s < n_act; ++s) Mx = fmaxf(Mx, __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s].x));
-              for (int s = 0; s < n_act; ++s) {
-                const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + s]);
-                const float w = ml.y > 0.f ? fast_exp2(ml.x - Mx) : 0.f;
-                L += ml.y * w;
-                acc += __ldcg(p.part_o + ((size_t)bh * p.nsplit + s) * 128 + tt) * w;
+              for (int j = 0; j < 8; ++j) {
+                const int s = s0 + j;
+                const float wa = __shfl_sync(0xffffffffu, w0, s & 31), wb = __shfl_sync(0xffffffffu, w1, s & 31);
+                const float w = s < 32 ? wa : wb;
+                acc.x = fmaf(v[j].x, w, acc.x); acc.y = fmaf(v[j].y, w, acc.y);
+                acc.z = fmaf(v[j].z, w, acc.z); acc.w = fmaf(v[j].w, w, acc.w);
               }
             }
-            p.attn[(size_t)b * p.H + h * 128 + tt] = __float2bfloat16_rn(L > 0.f ? acc / L : 0.f);
-            if (tt == 0) p.attn_counters[bh] = 0;
+            const float inv = L > 0.f ? 1.f / L : 0.f;
+            *reinterpret_cast<uint2*>(p.attn + (size_t)b * p.H + h * 128 + lane * 4) =
+                make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
+            if (lane == 0) p.attn_counters[bh] = 0;
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + tm) : "memory");   // scratch reuse by the next item
         }
       }
       t_attn += clock64() - t0;
@@ -370,26 +407,36 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
     } else {
       // ------------------------------ weight phase ------------------------------
       const bool norm = (d.type == PH_QKV || d.type == PH_GATEUP || d.type == PH_LOGITS);
+      const int rows_u = d.rows, KCp = d.kc;
+      const int row_stride = KCp * 2 + PAD;
       if (!is_fin) {
-        float sq[BMAX];
+        // the activation rows [B, K] (written by other CTAs before the grid barrier) arrive by bulk copy: one thread issues B
+        // copies, everybody waits on the mbarrier -- one L2 round trip whatever K is, no per-thread load loop
+        if (ct == 0) {
+          fence_proxy_async_global();
+          mbar_expect_tx(x_bar, (uint32_t)p.B * d.K * 2);
+          for (int b = 0; b < p.B; ++b) bulk_load_1d(xs + (size_t)b * xs_stride, d.x_in + (size_t)b * d.K, (uint32_t)d.K * 2, x_bar);
+        }
+        mbar_wait(x_bar, xph);
+        if (norm) {
+          float sq[BMAX];
 #pragma unroll
-        for (int b = 0; b < BMAX; ++b) sq[b] = 0.f;
-        const int chunks = d.K >> 3;
-        for (int c = ct; c < chunks; c += M::CONSUMERS) {
+          for (int b = 0; b < BMAX; ++b) sq[b] = 0.f;
+          const int chunks = d.K >> 3;
+          for (int c = ct; c < chunks; c += M::CONSUMERS) {
 #pragma unroll
-          for (int b = 0; b < BMAX; ++b) {
-            uint4 w = make_uint4(0, 0, 0, 0);
-            if (b < p.B) w = ldcg_v4(d.x_in + (size_t)b * d.K + c * 8);
-            *reinterpret_cast<uint4*>(xs + (size_t)b * xs_stride + c * 8) = w;
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            for (int b = 0; b < BMAX; ++b) {
+              if (b < p.B) {
+                const uint4 w = *reinterpret_cast<const uint4*>(xs + (size_t)b * xs_stride + c * 8);
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float a = bf16_lo(ww[i]), bb = bf16_hi(ww[i]);
-              sq[b] += a * a + bb * bb;
+                for (int i = 0; i < 4; ++i) {
+                  const float a = bf16_lo(ww[i]), bb = bf16_hi(ww[i]);
+                  sq[b] += a * a + bb * bb;
+                }
+              }
             }
           }
-        }
-        if (norm) {
 #pragma unroll
           for (int b = 0; b < BMAX; ++b) {
             const float v = warp_sum(sq[b]);
@@ -397,47 +444,48 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
           }
         }
       }
-      asm volatile("bar.sync 2, 544;" ::: "memory");
-      if (norm && !is_fin && ct < BMAX) {
-        float t = 0.f;
-        for (int w = 0; w < 16; ++w) t += wred[w * BMAX + ct];
-        rstd_s[ct] = rsqrtf(t / d.K + p.eps);
+      xph ^= 1;
+      if (norm) {
+        asm volatile("bar.sync 2, 544;" ::: "memory");
+        if (!is_fin && ct < BMAX) {
+          float t = 0.f;
+          for (int w = 0; w < 16; ++w) t += wred[w * BMAX + ct];
+          rstd_s[ct] = rsqrtf(t / d.K + p.eps);
+        }
+        asm volatile("bar.sync 2, 544;" ::: "memory");
       }
-      asm volatile("bar.sync 2, 544;" ::: "memory");
       t_stage += clock64() - t0;
       if (dbg_o != nullptr) dbg_o[8 + 3 * d.type] += clock64() - t0;
       t0 = clock64();
-      const int n_groups = (d.N + ROWS - 1) / ROWS;
-      const int n_slices = (d.K + KC - 1) / KC;
+      const int n_groups = (d.N + rows_u - 1) / rows_u;
+      const int n_slices = (d.K + KCp - 1) / KCp;
       if (!is_fin) {
         // ===== compute warps: ring stage x activation rows -> per-warp partials -> handoff slot =====
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
-          const int n0 = g * ROWS;
-          const int rows = min(ROWS, d.N - n0);
+          const int n0 = g * rows_u;
+          const int rows = min(rows_u, d.N - n0);
           const int slot = unit_no & (M::RED_SLOTS - 1);
           const uint32_t round = (unit_no / M::RED_SLOTS) & 1;
           if constexpr (kTC) {
             // ---- tensor-core consumer (B = 2..4): mma.sync m16n8k16 with A = activation rows (batch on M, rows >= B zero)
-            // and B = 8 weight rows (N).  Lane (g = lane/4, t = lane%4) loads 16 contiguous bytes x[g][k..k+7] and
-            // W[g][k..k+7]; both operands use the same k permutation, so two MMAs consume them.
+            // and B = up to 8 weight rows (N).  Lane (g = lane/4, t = lane%4) loads 16 contiguous bytes x[g][k..k+7] and
+            // W[g][k..k+7]; both operands use the same k permutation, so two MMAs consume them.  The 32-wide k blocks of a
+            // stage are dealt round-robin to the 16 warps.
             const int gq = lane >> 2, tq = lane & 3;
             float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool w_ok = gq < rows, x_ok = gq < p.B;
             for (int s = 0; s < n_slices; ++s) {
-              const int kc = min(KC, d.K - s * KC);
+              const int kc = min(KCp, d.K - s * KCp);
               mbar_wait(&full_bar[st], ph);
-              const uint8_t* wrow = ring + (size_t)st * STAGE_B + gq * ROW_STRIDE;
-              const __nv_bfloat16* xrow = xs + (size_t)gq * xs_stride + (size_t)s * KC;
-              const bool w_ok = gq < rows, x_ok = gq < p.B;
-#pragma unroll
-              for (int j = 0; j < KC / (16 * 32); ++j) {
-                const int k = cw * (KC / 16) + j * 32;       // this warp's 32-wide k block (warp-uniform bound check)
-                if (k < kc) {
-                  uint4 wb = make_uint4(0, 0, 0, 0), xa = make_uint4(0, 0, 0, 0);
-                  if (w_ok) wb = *reinterpret_cast<const uint4*>(wrow + (k + tq * 8) * 2);
-                  if (x_ok) xa = *reinterpret_cast<const uint4*>(xrow + k + tq * 8);
-                  mma_m16n8k16_bf16(dacc, xa.x, 0u, xa.y, 0u, wb.x, wb.y);
-                  mma_m16n8k16_bf16(dacc, xa.z, 0u, xa.w, 0u, wb.z, wb.w);
-                }
+              const uint8_t* wrow = ring + (size_t)st * p.stage_bytes + gq * row_stride;
+              const __nv_bfloat16* xrow = xs + (size_t)gq * xs_stride + (size_t)s * KCp;
+#pragma unroll 4
+              for (int k = cw * 32; k < kc; k += 16 * 32) {
+                uint4 wb = make_uint4(0, 0, 0, 0), xa = make_uint4(0, 0, 0, 0);
+                if (w_ok) wb = *reinterpret_cast<const uint4*>(wrow + (k + tq * 8) * 2);
+                if (x_ok) xa = *reinterpret_cast<const uint4*>(xrow + k + tq * 8);
+                mma_m16n8k16_bf16(dacc, xa.x, 0u, xa.y, 0u, wb.x, wb.y);
+                mma_m16n8k16_bf16(dacc, xa.z, 0u, xa.w, 0u, wb.z, wb.w);
               }
               __syncwarp();
               if (lane == 0) mbar_arrive(&empty_bar[st]);
@@ -458,21 +506,21 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
 #pragma unroll
           for (int i = 0; i < NV; ++i) acc[i] = 0.f;
           for (int s = 0; s < n_slices; ++s) {
-            const int kc = min(KC, d.K - s * KC);
+            const int kc = min(KCp, d.K - s * KCp);
             mbar_wait(&full_bar[st], ph);
-            if (ct * 8 < kc) {
-              const uint8_t* src = ring + (size_t)st * STAGE_B + ct * 16;
+            for (int c8 = ct * 8; c8 < kc; c8 += M::CONSUMERS * 8) {
+              const uint8_t* src = ring + (size_t)st * p.stage_bytes + c8 * 2;
               float xf[BMAX][8];
 #pragma unroll
               for (int b = 0; b < BMAX; ++b) {
-                const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * xs_stride + (size_t)s * KC + ct * 8);
+                const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * xs_stride + (size_t)s * KCp + c8);
                 xf[b][0] = bf16_lo(xv.x); xf[b][1] = bf16_hi(xv.x); xf[b][2] = bf16_lo(xv.y); xf[b][3] = bf16_hi(xv.y);
                 xf[b][4] = bf16_lo(xv.z); xf[b][5] = bf16_hi(xv.z); xf[b][6] = bf16_lo(xv.w); xf[b][7] = bf16_hi(xv.w);
               }
 #pragma unroll
               for (int r = 0; r < ROWS; ++r) {
                 if (r < rows) {
-                  const uint4 wv = *reinterpret_cast<const uint4*>(src + r * ROW_STRIDE);
+                  const uint4 wv = *reinterpret_cast<const uint4*>(src + r * row_stride);
                   const float wf[8] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y),
                                        bf16_lo(wv.z), bf16_hi(wv.z), bf16_lo(wv.w), bf16_hi(wv.w)};
 #pragma unroll
@@ -496,11 +544,11 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         // ===== finalize warp: sum the 16 partials of each unit, fused epilogue =====
         constexpr unsigned kMask = (NV == 32) ? 0xffffffffu : ((1u << NV) - 1u);
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
-          const int n0 = g * ROWS;
+          const int n0 = g * rows_u;
           const int slot = unit_no & (M::RED_SLOTS - 1);
           const uint32_t round = (unit_no / M::RED_SLOTS) & 1;
           const int r = lane / BMAX, b = lane % BMAX, n = n0 + r;
-          const bool ok = lane < NV && b < p.B && n < d.N;
+          const bool ok = lane < NV && r < rows_u && b < p.B && n < d.N;
           // operands of the epilogue are fetched while the compute warps are still busy with this unit
           float pre0 = 0.f, pre1 = 0.f;
           if (ok) {
