@@ -1,0 +1,209 @@
+// Probe for a tcgen05 consumer of the decode step at B = 2..4 (instead of legacy mma.sync, which sustains only ~1 m16n8k16 per
+// 40 cycles per SM sub-partition on this part):
+//   D[64 x 8] (TMEM) += A[64 x 16] * B[8 x 16]^T,  A = the activation rows (batch rows 0..B-1; rows >= 8 read whatever follows in
+//   shared memory -- their D rows are never looked at), B = 8 weight rows of the ring stage, both K-major SWIZZLE_128B.
+//   * the weight stage arrives in the canonical UMMA layout by ONE 3-D tensor TMA copy per stage:
+//     tensor {64 (k within a panel), N (rows), K/64 (panels)}, box {64, 8, panels per stage} -> smem [panel][8 rows][128 B]
+//   * NI issuer threads (lane 0 of NI warps) each take every NI-th 16-wide k step of a stage and accumulate into their own 8 TMEM
+//     columns; tcgen05.commit -> the stage's empty barrier (count NI) and, after the unit's last stage, its accumulator barrier
+//   * a finalize warp (TMEM lane quadrant 0) reads the NI x 8 columns of lanes 0..B-1 and sums them.
+// Checks the result against a CPU reference and reports the streaming rate.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_probe tools/umma_probe.cu -lcuda && tools/umma_probe
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../valley_b200/csrc/common.cuh"
+using namespace vly;
+
+struct PP {
+  int N, K, KC, n_stages, n_issuers, B;
+  const __nv_bfloat16* x;   // [B, K]
+  float* out;               // [B, N]
+};
+
+constexpr int ROWS = 8, ACC_SLOTS = 4;
+
+__global__ void __launch_bounds__(576, 1) umma_stream(const __grid_constant__ CUtensorMap tmap, const PP p) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const uint32_t base = smem_u32(sm);
+  if (base & 1023u) __trap();
+  const int stage_b = ROWS * p.KC * 2;                       // [KC/64 panels][8 rows][128 B]
+  uint8_t* ring = sm;
+  uint8_t* xsw = ring + (size_t)p.n_stages * stage_b;        // [K/64 panels][8 rows][128 B], swizzled
+  const size_t x_bytes = (size_t)(p.K / 64) * 1024;
+  uint64_t* full = reinterpret_cast<uint64_t*>(xsw + x_bytes + 8192);     // (+8 KB: rows >= 8 of the last panels read past the block)
+  uint64_t* empty = full + 8;
+  uint64_t* acc_full = empty + 8;
+  uint64_t* acc_empty = acc_full + ACC_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_SLOTS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.n_issuers); }
+    for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&acc_full[i], p.n_issuers); mbar_init(&acc_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
+  // stage x into the swizzled A layout (rows >= B are left as they are: their products land in D rows nobody reads)
+  for (int i = tid; i < p.B * (p.K / 8); i += blockDim.x) {
+    const int b = i / (p.K / 8), c = i % (p.K / 8);          // chunk c = 8 columns
+    const uint4 v = *reinterpret_cast<const uint4*>(p.x + (size_t)b * p.K + c * 8);
+    const int panel = c >> 3, c16 = c & 7;
+    *reinterpret_cast<uint4*>(xsw + (size_t)panel * 1024 + b * 128 + ((c16 ^ (b & 7)) << 4)) = v;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_groups = p.N / ROWS, n_slices = p.K / p.KC, ksteps = p.KC / 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x)
+        for (int s = 0; s < n_slices; ++s) {
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_expect_tx(&full[st], (uint32_t)stage_b);
+          tma_load_3d(ring + (size_t)st * stage_b, &tmap, &full[st], 0, g * ROWS, s * (p.KC / 64));
+          if (++st == p.n_stages) { st = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp >= 1 && warp <= p.n_issuers) {
+    if (lane == 0) {
+      const int me = warp - 1;
+      constexpr uint32_t idesc = make_idesc_bf16(64, 8);
+      int st = 0;
+      uint32_t ph = 0;
+      unsigned unit_no = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
+        const int slot = unit_no % ACC_SLOTS;
+        mbar_wait(&acc_empty[slot], ((unit_no / ACC_SLOTS) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * 64 + me * 8;
+        bool first = true;
+        for (int s = 0; s < n_slices; ++s) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t b_addr = base + st * stage_b;
+          const uint32_t a_addr = smem_u32(xsw) + (uint32_t)(s * (p.KC / 64)) * 1024;
+          for (int ks = me; ks < ksteps; ks += p.n_issuers) {
+            const uint32_t off = (uint32_t)(ks >> 2) * 1024 + (ks & 3) * 32;
+            tc_mma_bf16(d_tmem, make_smem_desc_sw128(a_addr + off, 16, 1024), make_smem_desc_sw128(b_addr + off, 16, 1024), idesc, !first);
+            first = false;
+          }
+          tc_commit(&empty[st]);
+          if (++st == p.n_stages) { st = 0; ph ^= 1; }
+        }
+        tc_commit(&acc_full[slot]);
+      }
+    }
+  } else if (warp == 16) {
+    unsigned unit_no = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
+      const int slot = unit_no % ACC_SLOTS;
+      mbar_wait(&acc_full[slot], (unit_no / ACC_SLOTS) & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_base + slot * 64, v0);
+      tmem_ld_32x32(tmem_base + slot * 64 + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      if (lane < p.B) {
+        for (int r = 0; r < ROWS; ++r) {
+          float t = 0.f;
+          for (int i = 0; i < p.n_issuers; ++i) t += __uint_as_float(i < 4 ? v0[i * 8 + r] : v1[(i - 4) * 8 + r]);
+          p.out[(size_t)lane * p.N + g * ROWS + r] = t;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main() {
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  PFN_encodeTiled encode = (PFN_encodeTiled)fn;
+  const int B = 4;
+  cudaFuncSetAttribute(umma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  struct Cfg { int K, KC; };
+  for (Cfg c : {Cfg{5120, 2560}, Cfg{5120, 1280}, Cfg{4608, 2304}, Cfg{4096, 2048}}) {
+    const size_t bytes = (size_t)4 << 30;
+    const int N = (int)(bytes / ((size_t)c.K * 2) / (148 * ROWS) * (148 * ROWS));
+    __nv_bfloat16 *W, *x;
+    float* out;
+    cudaMalloc(&W, (size_t)N * c.K * 2);
+    cudaMalloc(&x, (size_t)B * c.K * 2);
+    cudaMalloc(&out, (size_t)B * N * 4);
+    // deterministic pseudo-random fill on the host for the part that is checked, pattern fill elsewhere
+    const int n_check = 148 * ROWS * 2;
+    std::vector<__nv_bfloat16> hW((size_t)n_check * c.K), hx((size_t)B * c.K);
+    uint32_t s = 12345;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xffff) / 65536.f - 0.5f; };
+    for (auto& v : hW) v = __float2bfloat16(rnd() * 0.1f);
+    for (auto& v : hx) v = __float2bfloat16(rnd());
+    cudaMemset(W, 0, (size_t)N * c.K * 2);
+    cudaMemcpy(W, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(x, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice);
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {64, (cuuint64_t)N, (cuuint64_t)(c.K / 64)};
+    cuuint64_t strides[2] = {(cuuint64_t)c.K * 2, 128};
+    cuuint32_t box[3] = {64, ROWS, (cuuint32_t)(c.KC / 64)};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, W, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("K=%d KC=%d N=%d: tensor map encode -> %d\n", c.K, c.KC, N, (int)r);
+    if (r != CUDA_SUCCESS) continue;
+    for (int stages : {3, 4}) for (int ni : {4, 8}) {
+      PP p;
+      p.N = N; p.K = c.K; p.KC = c.KC; p.n_stages = stages; p.n_issuers = ni; p.B = B; p.x = x; p.out = out;
+      const size_t smem = (size_t)stages * ROWS * c.KC * 2 + (size_t)(c.K / 64) * 1024 + 8192 + 512;
+      if (smem > 227 * 1024) continue;
+      float best = 0.f;
+      for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        umma_stream<<<148, 576, smem>>>(tm, p);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const float gbs = (float)((double)N * c.K * 2 / ms / 1e6);
+        if (gbs > best) best = gbs;
+      }
+      cudaError_t err = cudaGetLastError();
+      std::vector<float> ho((size_t)B * N);
+      cudaMemcpy(ho.data(), out, ho.size() * 4, cudaMemcpyDeviceToHost);
+      double max_err = 0, max_ref = 0;
+      for (int b = 0; b < B; ++b)
+        for (int n = 0; n < n_check; ++n) {
+          double ref = 0;
+          for (int k = 0; k < c.K; ++k) ref += (double)__bfloat162float(hW[(size_t)n * c.K + k]) * __bfloat162float(hx[(size_t)b * c.K + k]);
+          max_err = fmax(max_err, fabs(ref - ho[(size_t)b * N + n]));
+          max_ref = fmax(max_ref, fabs(ref));
+        }
+      printf("    stages %d issuers %d: %7.1f GB/s   max|err| %.3e (max|ref| %.3f)  %s\n", stages, ni, best, max_err, max_ref, cudaGetErrorString(err));
+      if (err != cudaSuccess) return 1;
+    }
+    cudaFree(W); cudaFree(x); cudaFree(out);
+  }
+  return 0;
+}

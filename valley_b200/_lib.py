@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvalley_b200.so")
+# VLY_LIB_PATH: A/B measurements against another build of the same ABI (tools/); the product always loads the in-tree library
+LIB_PATH = os.environ.get("VLY_LIB_PATH") or os.path.join(_HERE, "lib", "libvalley_b200.so")
 
 
 class VlyConfig(C.Structure):

@@ -254,6 +254,27 @@ static int make_tmap_3d(vly_ctx* c, CUtensorMap* m, const void* ptr, uint64_t d0
   return VLY_OK;
 }
 
+// ---- launch helper: optional programmatic dependent launch (the kernel's prologue overlaps the previous kernel's tail; kernels
+// launched this way call griddepcontrol.wait before they touch the previous kernel's data).  VLY_NO_PDL=1 disables it. ----
+static bool pdl_enabled() {
+  static const bool on = getenv("VLY_NO_PDL") == nullptr;
+  return on;
+}
+template <typename Kern, typename... Args>
+static cudaError_t launch_ex(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------------
@@ -283,22 +304,23 @@ static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W
       cfg.blockDim = dim3(Cfg::THREADS);
       cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
       cfg.stream = st;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = pdl_enabled() ? 2 : 1;
       CK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true>, ta, tb2, p));
       c->launches++;
       return VLY_OK;
     }
   }
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  gemm_tc_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  CK(launch_ex(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, true, ta, tb, p));
   c->launches++;
-  CKL();
   return VLY_OK;
 }
 template <int EPI>
@@ -308,12 +330,16 @@ static int launch_gemm(vly_ctx* c, int bn, const bf16* A, long long lda, const b
   return launch_gemm_t<128, EPI>(c, A, lda, W, ldw, p, st);
 }
 static inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
-// Small problems: a 128 x 256 tiling that covers less than ~2/3 of the SMs is re-tiled 128 x 128 (twice the CTAs, half the
-// main loop per CTA).  M-dependent, so callers that exchange row statistics compute it ONCE per (N, M) and pass it around.
+// Tile width by wave efficiency: a persistent launch runs ceil(tiles / SMs) rounds, so what counts is how full the last round
+// is.  M = 2056 (8 frames), N = 3072: 128 x 256 tiles -> 204 tiles = 2 rounds at 69 %; 128 x 128 -> 408 tiles = 3 half-size rounds
+// at 92 %.  256-wide tiles are kept when they are within 5 % (better operand reuse per SM).  M-dependent, so callers that
+// exchange row statistics compute it ONCE per (N, M) and pass it around.
 static inline int pick_bn_m(const vly_ctx* c, int N, int M) {
   if (N % 256 != 0) return 128;
-  const int tiles256 = cdiv(M, 128) * (N / 256);
-  return (tiles256 * 3 < c->num_sms * 2) ? 128 : 256;
+  const long long t256 = (long long)cdiv(M, 128) * (N / 256), t128 = 2 * t256;
+  const double e256 = (double)t256 / ((double)cdiv(t256, c->num_sms) * c->num_sms);
+  const double e128 = (double)t128 / ((double)cdiv(t128, c->num_sms) * c->num_sms);
+  return (e128 > e256 * 1.05) ? 128 : 256;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -764,9 +790,8 @@ static int launch_vit_attention(vly_ctx* c, const bf16* qkv, int F, bf16* out, c
     TRY(ensure_smem_attr(c->cfg.device, vit_attention_pp_kernel, VitAttnPPCfg::SMEM_BYTES));
     CUtensorMap tx;
     TRY(make_tmap_2d(c, &tx, qkv, 3 * D, (uint64_t)F * tokens, (uint64_t)3 * D * 2, 64, 1, /*swizzle128=*/false));   // single rows, read linearly
-    vit_attention_pp_kernel<<<grid, VitAttnPPCfg::THREADS, VitAttnPPCfg::SMEM_BYTES, st>>>(tq, tx, p);
+    CK(launch_ex(vit_attention_pp_kernel, dim3(grid), dim3(VitAttnPPCfg::THREADS), VitAttnPPCfg::SMEM_BYTES, st, true, tq, tx, p));
     c->launches++;
-    CKL();
     return VLY_OK;
   }
   vit_attention_kernel<<<grid, VitAttnCfg::THREADS, VitAttnCfg::SMEM_BYTES, st>>>(tq, tkv, p);
@@ -1171,9 +1196,11 @@ static void pick_phase_geometry(int bmax, size_t ring_budget, int N, int K, int 
   const int pad = tc ? MegaCfg::PAD_TC : 0, gran = tc ? 64 : 8;
   static const int env_kb = getenv("VLY_MEGA_STAGE_KB") ? atoi(getenv("VLY_MEGA_STAGE_KB")) : 0;
   static const int env_rows = getenv("VLY_MEGA_ROWS") ? atoi(getenv("VLY_MEGA_ROWS")) : 0;
-  size_t target = env_kb > 0 ? (size_t)env_kb * 1024 : ring_budget / 5;
-  if (target < 16 * 1024) target = 16 * 1024;
-  if (target > 48 * 1024) target = 48 * 1024;
+  // measured (same-box A/B of the real step, profiles/decode_ab_r02.txt): CUDA-core path -- 4 slots of 32-41 KB beat 3 (more
+  // bytes in flight) and 6 (the grid barriers queue behind the extra prefetch traffic); tensor-core path -- 8 rows x ~2048 columns
+  size_t target = env_kb > 0 ? (size_t)env_kb * 1024 : (tc ? 33 * 1024 + 512 : 41 * 1024);
+  if (target > ring_budget / 2) target = ring_budget / 2;
+  if (target < 8 * 1024) target = 8 * 1024;
   auto kc_for = [&](int rows) {
     const int cap = (int)((target / rows - pad) / 2);
     const int ns = cdiv(K, cap > gran ? cap : gran);
@@ -1183,8 +1210,8 @@ static void pick_phase_geometry(int bmax, size_t ring_budget, int N, int K, int 
   int rows = max_rows;
   if (env_rows > 0) rows = env_rows > max_rows ? max_rows : env_rows;
   else {
-    if (kc_for(rows) * 2 < 4096 && K * 2 >= 4096) rows = max_rows / 2;            // keep every bulk copy >= 4 KB
-    if (rows == max_rows) {
+    if (kc_for(rows) * 2 < 3072 && K * 2 >= 3072) rows = max_rows / 2;            // keep every bulk copy >= 3 KB
+    if (rows == max_rows && !tc) {        // (tensor-core path: half-filled HMMAs cost more than the imbalance they would remove)
       const long long load_full = (long long)cdiv(cdiv(N, max_rows), num_sms) * max_rows;
       const long long load_half = (long long)cdiv(cdiv(N, max_rows / 2), num_sms) * (max_rows / 2);
       if (load_half * 100 < load_full * 97) rows = max_rows / 2;                  // at least 3 % shorter critical path
@@ -1213,7 +1240,7 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
     int ns = (2 * c->num_sms + batch * nH - 1) / (batch * nH);
     kv->nsplit = ns < 1 ? 1 : (ns > 16 ? 16 : ns);
   } else {
-    kv->nsplit = kv->Smax / MegaCfg::ATTN_KEYS; // capacity of the split dimension: the persistent kernel uses 32-key items, the
+    kv->nsplit = kv->Smax / MegaCfg::ATTN_KEYS_MIN; // capacity of the split dimension: the persistent kernel uses 16/32-key items, the
                                                 // per-op kernel fixed 64-key splits (it only touches the first Smax / 64 slots)
   }
   kv->gemv_grid = 2 * c->num_sms;
@@ -1275,10 +1302,15 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
     PhaseDesc d = {};
     d.type = PH_LOGITS; d.N = V; d.K = H; d.W = c->lm_head; d.x_in = kv->x; d.out = nullptr; add(d);
     kv->stage_bytes = (kv->stage_bytes + 127) & ~127;
-    for (PhaseDesc& q : ph) {          // stages of this phase's size that make ~116 KB of copies outstanding per SM
+    // Stages of this phase's size kept in flight: ~100 KB of bulk copies outstanding per SM saturate HBM; every byte beyond
+    // that only lengthens the queues the latency-critical traffic (grid barrier, activation staging, attention) waits in --
+    // measured: 128 KB in flight made every barrier ~1 us slower at an unchanged streaming rate.  The ring may hold more slots
+    // than are in flight: they absorb the consumers' hand-back latency.  VLY_MEGA_INFLIGHT_KB overrides.
+    static const int env_if = getenv("VLY_MEGA_INFLIGHT_KB") ? atoi(getenv("VLY_MEGA_INFLIGHT_KB")) : 100;
+    for (PhaseDesc& q : ph) {
       if (q.type == PH_ATTN) continue;
       const int sb = q.rows * (q.kc * 2 + pad);
-      q.inflight = (116 * 1024 + sb / 2) / sb;
+      q.inflight = (env_if * 1024 + sb / 2) / sb;
       if (q.inflight < 2) q.inflight = 2;
     }
     if (getenv("VLY_MEGA_DBG")) {
@@ -1398,22 +1430,6 @@ static int launch_gemv(vly_ctx* c, GemvParams p, int grid, cudaStream_t st) {
 }
 
 // ---- generation-2 decode launchers (TMA ring + programmatic dependent launch) ----
-template <typename Kern, typename... Args>
-static cudaError_t launch_ex(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  static const bool no_pdl = getenv("VLY_NO_PDL") != nullptr;
-  cfg.numAttrs = (pdl && !no_pdl) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
 template <int MODE>
 static int launch_gemv_ring(vly_ctx* c, GemvParams p, bool pdl, cudaStream_t st) {
   const int bmax = p.B <= 1 ? 1 : (p.B <= 2 ? 2 : 4);
@@ -1544,9 +1560,8 @@ static int launch_prefill_attention(vly_ctx* c, vly_kv* kv, const bf16* qbuf, in
   p.scale_log2e = 0.08838834764831845f * 1.4426950408889634f;
   p.key_bits = kv->masked ? kv->key_bits : nullptr; p.mask_words = kv->mask_words();
   const int n_qt = cdiv(S, 128);
-  llama_prefill_attention_kernel<<<B * nH * n_qt, PrefillAttnCfg::THREADS, PrefillAttnCfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  CK(launch_ex(llama_prefill_attention_kernel, dim3(B * nH * n_qt), dim3(PrefillAttnCfg::THREADS), PrefillAttnCfg::SMEM_BYTES, st, true, tq, tk, tv, p));
   c->launches++;
-  CKL();
   return VLY_OK;
 }
 
@@ -1673,7 +1688,8 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   {
     // depth of the ring and number of stages kept in flight: see pick_phase_geometry.  VLY_MEGA_STAGES / VLY_MEGA_INFLIGHT override.
     static const int want = getenv("VLY_MEGA_STAGES") ? atoi(getenv("VLY_MEGA_STAGES")) : 0;
-    if (want > 0 && n_stages > want) n_stages = want;
+    const int cap = want > 0 ? want : 4;            // deeper rings made every grid barrier slower (see pick_phase_geometry)
+    if (n_stages > cap) n_stages = cap;
     static const int inflight = getenv("VLY_MEGA_INFLIGHT") ? atoi(getenv("VLY_MEGA_INFLIGHT")) : 0;
     p.n_inflight = inflight > 0 ? inflight : n_stages;                        // (PhaseDesc::inflight is the per-phase value)
     if (p.n_inflight > n_stages) p.n_inflight = n_stages;

@@ -370,8 +370,10 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
+      pdl_wait();               // q and the appended K/V rows come from the QKV GEMM of this layer
       mbar_expect_tx(q_full, 2 * C::TILE_BYTES);
       tma_load_2d(smem + C::OFF_Q, &tma_q, q_full, h * 128, b * p.S + qt * 128);
       tma_load_2d(smem + C::OFF_Q + C::TILE_BYTES, &tma_q, q_full, h * 128 + 64, b * p.S + qt * 128);
@@ -634,8 +636,10 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_launch_dependents();      // (see gemm_tc_kernel: prologue overlaps the previous kernel's tail under programmatic launch)
   if (warp == 0) {
     if (lane == 0 && n_tiles > 0) {
+      pdl_wait();               // the QKV GEMM's output is read by the TMA loads below
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 256);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
       const uint64_t desc_q[2] = {make_smem_desc_sw128(base_u32 + C::OFF_Q, 16, 1024), make_smem_desc_sw128(base_u32 + C::OFF_Q + C::Q_BYTES, 16, 1024)};

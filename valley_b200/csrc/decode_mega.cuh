@@ -58,7 +58,7 @@ struct StepParams {
   float* part_o;                // [B*nH, nsplit, 128]
   float2* part_ml;              // [B*nH, nsplit]
   unsigned int* attn_counters;  // [B*nH]
-  int nsplit;                   // capacity of the split dimension (Smax / ATTN_KEYS)
+  int nsplit;                   // capacity of the split dimension (Smax / ATTN_KEYS_MIN)
   const uint32_t* key_bits;     // [B, mask_words] attention_mask, one bit per cache position (1 = attend)
   int mask_words;
   float* logits;                // [B, V]
@@ -86,7 +86,8 @@ struct MegaCfg {
   static constexpr int CONSUMERS = 512, THREADS = 576;   // producer warp + 16 compute warps + 1 finalize warp
   static constexpr int RED_SLOTS = 4;
   static constexpr int MAX_STAGES = 8;
-  static constexpr int ATTN_KEYS = 32;                   // keys per attention work item (one warp, two passes of 16)
+  static constexpr int ATTN_KEYS_MIN = 16;               // keys per attention work item: 16 (one pass) while every item finds a
+                                                         // free warp, else 32 (two passes); the split buffers hold Smax / 16
 };
 
 VLY_DEVINL uint4 ldcg_v4(const void* p) {
@@ -178,7 +179,10 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
       int wst = 0, issued = 0, confirmed = 0;
       uint32_t wph = 0;
       for (int pi = 0; pi < p.n_phases; ++pi) {
-        const PhaseDesc& d = p.phases[pi];
+        // by value: a reference would be re-read from global memory after every mbarrier asm ("memory" clobber), and the time the
+        // producer needs to re-arm a freed slot comes straight out of the bytes in flight
+        const PhaseDesc d = p.phases[pi];
+        if (pi + 2 < p.n_phases) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.phases + pi + 2));
         if (d.type == PH_ATTN) continue;
         const int rows_u = d.rows, KCp = d.kc;
         const int row_stride = KCp * 2 + PAD;
@@ -251,6 +255,10 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
   unsigned int unit_no = 0;           // running work-unit counter of this CTA: selects the handoff slot
   for (int pi = 0; pi < p.n_phases; ++pi) {
     const PhaseDesc d = p.phases[pi];
+    if (pi + 1 < p.n_phases && lane == 0) {     // the next descriptor (L1 does not survive a launch): its L2 latency hides behind this phase
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.phases + pi + 1));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(p.phases + pi + 1) + 64));
+    }
     t0 = clock64();
     if (d.type == PH_ATTN) {
       if (!is_fin) {
@@ -259,17 +267,20 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         // and 8 V rows of a lane are requested up front (one L2 / HBM round trip), scores are reduced with a transposing shuffle
         // tree (8 instead of 32 shuffles), softmax runs online in registers across the two passes of an item, P.V accumulates per
         // lane over its 8 head dims.  Items are dealt warp-major over the SMs so one layer's K/V is pulled by every SM at once.
+        // Item size: with few (sequence, head, 16-key) items -- short contexts, B = 1 -- every item gets its own warp and a single
+        // round trip to the cache; otherwise 32 keys per item (two passes) halve the partials the merge has to read.
         const int len = pos + 1;
-        const int n_act = (len + M::ATTN_KEYS - 1) / M::ATTN_KEYS;
+        const int ikeys = (p.B * p.nH * ((len + 15) >> 4) <= 16 * (int)gridDim.x) ? 16 : 32;
+        const int n_act = (len + ikeys - 1) / ikeys;
         const int items = p.B * p.nH * n_act;
         const int hl = lane & 15, hw = lane >> 4;
         for (int it = cw * gridDim.x + blockIdx.x; it < items; it += gridDim.x * 16) {
           const int split = it % n_act, bh = it / n_act;
           const int b = bh / p.nH, h = bh - b * p.nH;
-          const int k0 = split * M::ATTN_KEYS, nk = min(len - k0, M::ATTN_KEYS);
+          const int k0 = split * ikeys, nk = min(len - k0, ikeys);
           const __nv_bfloat16* kb = d.kcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
           const __nv_bfloat16* vb = d.vcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
-          const uint32_t kbits = __ldg(p.key_bits + (size_t)b * p.mask_words + split);     // one mask word per 32 keys
+          const uint32_t kbits = __ldg(p.key_bits + (size_t)b * p.mask_words + (k0 >> 5)) >> (k0 & 31);   // one mask bit per cache position
           float qf[8];
           {
             const uint4 w = ldcg_v4(p.q + (size_t)b * p.H + h * 128 + hl * 8);
@@ -364,35 +375,47 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
           if (lane == 0) last = (atomicAdd(p.attn_counters + bh, 1u) == (unsigned)n_act - 1);
           last = __shfl_sync(0xffffffffu, last, 0);
           if (last) {
-            // ---- merge of the n_act (<= 64) partials by the warp that arrived last: lane s holds (max, sum) of splits s, s + 32 ----
+            // ---- merge of the n_act (<= 128) partials by the warp that arrived last: lane s holds (max, sum) of splits s + 32 i.
+            // The first batch of partial outputs is requested together with the (max, sum) pairs: one L2 round trip, not two.
             __threadfence();
-            float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
-            if (lane < n_act) {
-              const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane]);
-              m0 = ml.x; l0 = ml.y;
-            }
-            if (lane + 32 < n_act) {
-              const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane + 32]);
-              m1 = ml.x; l1 = ml.y;
-            }
-            const float Mx = warp_max(fmaxf(m0, m1));
-            const float w0 = l0 > 0.f ? fast_exp2(m0 - Mx) : 0.f;                 // a fully masked split has m = -inf, l = 0
-            const float w1 = l1 > 0.f ? fast_exp2(m1 - Mx) : 0.f;
-            const float L = warp_sum(l0 * w0 + l1 * w1);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* pb = p.part_o + (size_t)bh * p.nsplit * 128 + lane * 4;
-            for (int s0 = 0; s0 < n_act; s0 += 8) {
-              float4 v[8];
+            float4 v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                v[j] = (s0 + j < n_act) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)(s0 + j) * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 8; ++j)
+              v[j] = (j < n_act) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float mv[4], lv[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              mv[i] = -INFINITY;
+              lv[i] = 0.f;
+              if (lane + 32 * i < n_act) {
+                const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane + 32 * i]);
+                mv[i] = ml.x;
+                lv[i] = ml.y;
+              }
+            }
+            const float Mx = warp_max(fmaxf(fmaxf(mv[0], mv[1]), fmaxf(mv[2], mv[3])));
+            float lw = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              wv[i] = lv[i] > 0.f ? fast_exp2(mv[i] - Mx) : 0.f;                  // a fully masked split has m = -inf, l = 0
+              lw += lv[i] * wv[i];
+            }
+            const float L = warp_sum(lw);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s0 = 0; s0 < n_act; s0 += 8) {
+              const int gi = s0 >> 5;
+              const float wsel = gi == 0 ? wv[0] : (gi == 1 ? wv[1] : (gi == 2 ? wv[2] : wv[3]));
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const int s = s0 + j;
-                const float wa = __shfl_sync(0xffffffffu, w0, s & 31), wb = __shfl_sync(0xffffffffu, w1, s & 31);
-                const float w = s < 32 ? wa : wb;
+                const float w = __shfl_sync(0xffffffffu, wsel, (s0 + j) & 31);
                 acc.x = fmaf(v[j].x, w, acc.x); acc.y = fmaf(v[j].y, w, acc.y);
                 acc.z = fmaf(v[j].z, w, acc.z); acc.w = fmaf(v[j].w, w, acc.w);
+              }
+              if (s0 + 8 < n_act) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  v[j] = (s0 + 8 + j < n_act) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)(s0 + 8 + j) * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
             }
             const float inv = L > 0.f ? 1.f / L : 0.f;
@@ -472,25 +495,33 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
             // W[g][k..k+7]; both operands use the same k permutation, so two MMAs consume them.  The 32-wide k blocks of a
             // stage are dealt round-robin to the 16 warps.
             const int gq = lane >> 2, tq = lane & 3;
-            float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+            // (the legacy HMMA pipe of this part sustains ~1 m16n8k16 per 40 cycles per SM sub-partition -- tools/ringbw.cu -- so
+            //  the consumers, not HBM, bound this path; two accumulators keep the pair of MMAs of a k block independent)
+            float dacc[4] = {0.f, 0.f, 0.f, 0.f}, dacc1[4] = {0.f, 0.f, 0.f, 0.f};
             const bool w_ok = gq < rows, x_ok = gq < p.B;
             for (int s = 0; s < n_slices; ++s) {
               const int kc = min(KCp, d.K - s * KCp);
               mbar_wait(&full_bar[st], ph);
               const uint8_t* wrow = ring + (size_t)st * p.stage_bytes + gq * row_stride;
               const __nv_bfloat16* xrow = xs + (size_t)gq * xs_stride + (size_t)s * KCp;
+              // the 32-column k blocks of the stage are dealt to the 16 warps in contiguous runs
+              const int nblk = kc >> 5, bpw = (nblk + 15) >> 4;
+              const int kb0 = cw * bpw, kb1 = min(kb0 + bpw, nblk);
 #pragma unroll 4
-              for (int k = cw * 32; k < kc; k += 16 * 32) {
+              for (int kb = kb0; kb < kb1; ++kb) {
+                const int k = kb << 5;
                 uint4 wb = make_uint4(0, 0, 0, 0), xa = make_uint4(0, 0, 0, 0);
                 if (w_ok) wb = *reinterpret_cast<const uint4*>(wrow + (k + tq * 8) * 2);
                 if (x_ok) xa = *reinterpret_cast<const uint4*>(xrow + k + tq * 8);
                 mma_m16n8k16_bf16(dacc, xa.x, 0u, xa.y, 0u, wb.x, wb.y);
-                mma_m16n8k16_bf16(dacc, xa.z, 0u, xa.w, 0u, wb.z, wb.w);
+                mma_m16n8k16_bf16(dacc1, xa.z, 0u, xa.w, 0u, wb.z, wb.w);
               }
               __syncwarp();
               if (lane == 0) mbar_arrive(&empty_bar[st]);
               if (++st == p.n_stages) { st = 0; ph ^= 1; }
             }
+            dacc[0] += dacc1[0];
+            dacc[1] += dacc1[1];
             // lane (g < B, t) holds D[batch g][weight rows 2t, 2t+1] summed over this warp's k range
             mbar_wait(&red_empty[slot], round ^ 1);
             if (gq < BMAX) {

@@ -133,10 +133,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touches nothing the
+  // previous kernel of the stream produces, so when the launch carries the programmatic-serialisation attribute it overlaps that
+  // kernel's tail; the threads that read or overwrite its data (TMA producer, epilogue) wait for its completion first.
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -199,6 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int r_in_tile = quad * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
+    pdl_wait();                 // residual rows / row statistics of the previous kernel are read below
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int m_step = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
       const int m_blk = CG2 ? 2 * m_step + (int)cta_rank : m_step;
