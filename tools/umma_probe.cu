@@ -132,6 +132,130 @@ __global__ void __launch_bounds__(576, 1) umma_stream(const __grid_constant__ CU
   }
 }
 
+// ---- "diagonal-block" variant: ONE UMMA covers 8 weight rows x 8 panels (512 columns).  A = the weight stage seen as 64 rows:
+// row (c, r) = weight row r at panel c (8-row groups SBO = 1 KB apart = consecutive panels of the stage); B = the activation
+// block seen as 64 rows (c', b) the same way; D[(c, r)][(c', b)] accumulates W[r][panel c] . x[b][panel c'] -- the wanted dot
+// product is the sum over c of the diagonal blocks c = c'.  7/8 of the MACs are wasted; the tensor pipe has them to spare, and
+// an instruction now carries 8 KB / 4 of weights instead of 256 B.  Two issuers split the 4 k steps of a panel group; four
+// reader warps (one per TMEM lane quadrant; M = 64 puts rows 16q .. 16q + 15 on lanes 32q .. 32q + 15) sum the diagonal. ----
+__global__ void __launch_bounds__(576, 1) umma_diag_stream(const __grid_constant__ CUtensorMap tmap, const PP p) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const uint32_t base = smem_u32(sm);
+  if (base & 1023u) __trap();
+  const int stage_b = ROWS * p.KC * 2;
+  uint8_t* xsw = sm;                                         // [K/64 panels][8 rows][128 B]
+  const size_t x_bytes = (size_t)(p.K / 64) * 1024;
+  uint8_t* ring = sm + x_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.n_stages * stage_b);
+  uint64_t* empty = full + 8;
+  uint64_t* acc_full = empty + 8;
+  uint64_t* acc_empty = acc_full + ACC_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_SLOTS);
+  float* red = reinterpret_cast<float*>(tmem_slot + 4);      // [4 quadrants][8 rows][8 batch]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NI = 2;
+  if (tid == 0) {
+    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NI); }
+    for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&acc_full[i], NI); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < 8 * (p.K / 8); i += blockDim.x) {    // rows >= B zero here (the probe checks nothing there; any value works)
+    const int b = i / (p.K / 8), c = i % (p.K / 8);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (b < p.B) v = *reinterpret_cast<const uint4*>(p.x + (size_t)b * p.K + c * 8);
+    const int panel = c >> 3, c16 = c & 7;
+    *reinterpret_cast<uint4*>(xsw + (size_t)panel * 1024 + b * 128 + ((c16 ^ (b & 7)) << 4)) = v;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_groups = p.N / ROWS, n_slices = p.K / p.KC, pgroups = p.KC / 512;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x)
+        for (int s = 0; s < n_slices; ++s) {
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_expect_tx(&full[st], (uint32_t)stage_b);
+          tma_load_3d(ring + (size_t)st * stage_b, &tmap, &full[st], 0, g * ROWS, s * (p.KC / 64));
+          if (++st == p.n_stages) { st = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1 || warp == 2) {
+    if (lane == 0) {
+      const int me = warp - 1;
+      constexpr uint32_t idesc = make_idesc_bf16(64, 64);
+      int st = 0;
+      uint32_t ph = 0;
+      unsigned unit_no = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
+        const int slot = unit_no % ACC_SLOTS;
+        mbar_wait(&acc_empty[slot], ((unit_no / ACC_SLOTS) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * 128 + me * 64;
+        bool first = true;
+        for (int s = 0; s < n_slices; ++s) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(ring) + st * stage_b;                     // weights: the A operand
+          const uint32_t a_addr = smem_u32(xsw) + (uint32_t)(s * (p.KC / 64)) * 1024; // activations: the B operand
+          for (int pg = 0; pg < pgroups; ++pg) {
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint32_t off = (uint32_t)pg * 8192 + (uint32_t)(me * 2 + kk) * 32;
+              tc_mma_bf16(d_tmem, make_smem_desc_sw128(b_addr + off, 16, 1024), make_smem_desc_sw128(a_addr + off, 16, 1024), idesc, !first);
+              first = false;
+            }
+          }
+          tc_commit(&empty[st]);
+          if (++st == p.n_stages) { st = 0; ph ^= 1; }
+        }
+        tc_commit(&acc_full[slot]);
+      }
+    }
+  } else if (warp >= 13 && warp <= 16) {
+    const int q = warp & 3;                                   // TMEM lane quadrant of this warp
+    unsigned unit_no = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
+      const int slot = unit_no % ACC_SLOTS;
+      mbar_wait(&acc_full[slot], (unit_no / ACC_SLOTS) & 1);
+      tc_fence_after();
+      uint32_t v0[16], v1[16];
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + slot * 128 + q * 16;
+      tmem_ld_32x16(taddr, v0);                               // issuer 0's accumulator, columns 16q .. 16q + 15
+      tmem_ld_32x16(taddr + 64, v1);                          // issuer 1's
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      // lane l < 16: D row (c = 2q + (l >> 3), r = l & 7); its diagonal block is columns (l >> 3) * 8 + b of the 16 loaded
+      float t[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const float lo = __uint_as_float(v0[b]) + __uint_as_float(v1[b]);
+        const float hi = __uint_as_float(v0[8 + b]) + __uint_as_float(v1[8 + b]);
+        t[b] = (lane & 8) ? hi : lo;
+        t[b] += __shfl_xor_sync(0xffffffffu, t[b], 8);         // the two panels of this quadrant
+      }
+      // (a real kernel hands these to the epilogue warp through shared memory; the probe sums the 4 quadrants with atomics-free
+      //  two-phase writes: quadrant q writes its partial, quadrant 0 ... -- keep it simple: global atomicAdd on a zeroed output)
+      if (lane < 8)
+        for (int b = 0; b < p.B; ++b) atomicAdd(p.out + (size_t)b * p.N + g * ROWS + lane, t[b]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -142,11 +266,12 @@ int main() {
   PFN_encodeTiled encode = (PFN_encodeTiled)fn;
   const int B = 4;
   cudaFuncSetAttribute(umma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(umma_diag_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   struct Cfg { int K, KC; };
-  for (Cfg c : {Cfg{5120, 2560}, Cfg{5120, 1280}, Cfg{4608, 2304}, Cfg{4096, 2048}}) {
+  for (Cfg c : {Cfg{5120, 2560}, Cfg{5120, 1024}, Cfg{4608, 1536}, Cfg{4096, 2048}}) {
     const size_t bytes = (size_t)4 << 30;
     const int N = (int)(bytes / ((size_t)c.K * 2) / (148 * ROWS) * (148 * ROWS));
     __nv_bfloat16 *W, *x;
@@ -173,7 +298,7 @@ int main() {
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("K=%d KC=%d N=%d: tensor map encode -> %d\n", c.K, c.KC, N, (int)r);
     if (r != CUDA_SUCCESS) continue;
-    for (int stages : {3, 4}) for (int ni : {4, 8}) {
+    for (int stages : {3}) for (int ni : {8}) {
       PP p;
       p.N = N; p.K = c.K; p.KC = c.KC; p.n_stages = stages; p.n_issuers = ni; p.B = B; p.x = x; p.out = out;
       const size_t smem = (size_t)stages * ROWS * c.KC * 2 + (size_t)(c.K / 64) * 1024 + 8192 + 512;
@@ -203,6 +328,38 @@ int main() {
       printf("    stages %d issuers %d: %7.1f GB/s   max|err| %.3e (max|ref| %.3f)  %s\n", stages, ni, best, max_err, max_ref, cudaGetErrorString(err));
       if (err != cudaSuccess) return 1;
     }
+    if (c.KC % 512 == 0)
+      for (int stages : {3, 4, 5}) {
+        PP p;
+        p.N = N; p.K = c.K; p.KC = c.KC; p.n_stages = stages; p.n_issuers = 2; p.B = B; p.x = x; p.out = out;
+        const size_t smem = (size_t)stages * ROWS * c.KC * 2 + (size_t)(c.K / 64) * 1024 + 512 + 1024;
+        if (smem > 227 * 1024) continue;
+        float best = 0.f;
+        for (int rep = 0; rep < 3; ++rep) {
+          cudaMemset(out, 0, (size_t)B * N * 4);
+          cudaEventRecord(e0);
+          umma_diag_stream<<<148, 576, smem>>>(tm, p);
+          cudaEventRecord(e1);
+          cudaEventSynchronize(e1);
+          float ms;
+          cudaEventElapsedTime(&ms, e0, e1);
+          const float gbs = (float)((double)N * c.K * 2 / ms / 1e6);
+          if (gbs > best) best = gbs;
+        }
+        cudaError_t err = cudaGetLastError();
+        std::vector<float> ho((size_t)B * N);
+        cudaMemcpy(ho.data(), out, ho.size() * 4, cudaMemcpyDeviceToHost);
+        double max_err = 0, max_ref = 0;
+        for (int b = 0; b < B; ++b)
+          for (int n = 0; n < n_check; ++n) {
+            double ref = 0;
+            for (int k = 0; k < c.K; ++k) ref += (double)__bfloat162float(hW[(size_t)n * c.K + k]) * __bfloat162float(hx[(size_t)b * c.K + k]);
+            max_err = fmax(max_err, fabs(ref - ho[(size_t)b * N + n]));
+            max_ref = fmax(max_ref, fabs(ref));
+          }
+        printf("    DIAG stages %d (2 issuers): %7.1f GB/s   max|err| %.3e (max|ref| %.3f)  %s\n", stages, best, max_err, max_ref, cudaGetErrorString(err));
+        if (err != cudaSuccess) return 1;
+      }
     cudaFree(W); cudaFree(x); cudaFree(out);
   }
   return 0;

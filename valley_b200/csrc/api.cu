@@ -337,6 +337,7 @@ static inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
 static inline int pick_bn_m(const vly_ctx* c, int N, int M) {
   if (N % 256 != 0) return 128;
   const long long t256 = (long long)cdiv(M, 128) * (N / 256), t128 = 2 * t256;
+  if (t256 >= 3LL * c->num_sms) return 256;            // many rounds: the last one matters little, operand reuse matters more
   const double e256 = (double)t256 / ((double)cdiv(t256, c->num_sms) * c->num_sms);
   const double e128 = (double)t128 / ((double)cdiv(t128, c->num_sms) * c->num_sms);
   return (e128 > e256 * 1.05) ? 128 : 256;

@@ -182,7 +182,6 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         // by value: a reference would be re-read from global memory after every mbarrier asm ("memory" clobber), and the time the
         // producer needs to re-arm a freed slot comes straight out of the bytes in flight
         const PhaseDesc d = p.phases[pi];
-        if (pi + 2 < p.n_phases) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.phases + pi + 2));
         if (d.type == PH_ATTN) continue;
         const int rows_u = d.rows, KCp = d.kc;
         const int row_stride = KCp * 2 + PAD;
@@ -255,10 +254,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
   unsigned int unit_no = 0;           // running work-unit counter of this CTA: selects the handoff slot
   for (int pi = 0; pi < p.n_phases; ++pi) {
     const PhaseDesc d = p.phases[pi];
-    if (pi + 1 < p.n_phases && lane == 0) {     // the next descriptor (L1 does not survive a launch): its L2 latency hides behind this phase
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.phases + pi + 1));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(p.phases + pi + 1) + 64));
-    }
+    // (an L1 prefetch of the next descriptor was tried here: it made every grid barrier ~1 us SLOWER -- bisected on the GPU)
     t0 = clock64();
     if (d.type == PH_ATTN) {
       if (!is_fin) {
