@@ -704,3 +704,58 @@ def test_production_shapes_one_layer(spec_name, B):
     del m
     _models.pop((spec_name, 2), None)
     torch.cuda.empty_cache()
+
+
+def _decode_parity(spec_name, B, n=8, seed=0):
+    spec, sd, m = get(spec_name, seed)
+    cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
+    T = 2
+    ids, px = syn.make_prompt_ids(spec, B, T, 0, len_a=20, len_b=11), syn.make_pixels(B, T, 0)
+    with torch.no_grad():
+        r_tok, r_log = O.greedy_generate(sd, cfg, tok, ids, px, n, return_logits=True)
+    m.logits_all_positions = False
+    try:
+        out = m(input_ids=ids.cuda(), images=px.cuda())
+    finally:
+        m.logits_all_positions = True
+    cache, logs = out.past_key_values, [out.logits[:, -1].cpu()]
+    for i in range(1, n):
+        o = m(input_ids=r_tok[:, i - 1:i].cuda(), past_key_values=cache)
+        logs.append(o.logits[:, -1].cpu())
+    logs = torch.stack(logs, 1)
+    assert torch.isfinite(logs).all()
+    assert Hh.rel_fro(logs, r_log) < 2e-2, Hh.rel_fro(logs, r_log)
+    max_err = (logs - r_log).abs().max().item()
+    top2 = r_log.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * max_err
+    assert torch.equal(logs.argmax(-1)[safe], r_tok[safe])
+    gen = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n)[:, ids.shape[1]:].cpu()
+    gen2 = m.generate(input_ids=ids.cuda(), images=px.cuda(), max_new_tokens=n)[:, ids.shape[1]:].cpu()
+    assert torch.equal(gen, gen2)
+    for b in range(B):
+        for i in range(n):
+            if not safe[b, i]:
+                break
+            assert gen[b, i] == r_tok[b, i], (b, i)
+    return Hh.rel_fro(logs, r_log)
+
+
+@pytest.mark.parametrize("B", [2, 3, 4])
+def test_tcgen05_decode_consumer_full_and_tail_stages(B):
+    """decode_step_umma_kernel (B = 2..4, K multiples of 512): tiny-umma has intermediate_size 3584 = one 2560-column stage + a 1024-column
+    tail stage per work unit of down_proj (two sub-phases on one staged activation block); prefill + 8 teacher-forced steps +
+    free-running ids vs the oracle.  B = 1 on the same model runs decode_step_kernel<1> (the reference point)."""
+    _decode_parity("tiny-umma", B)
+
+
+def test_tcgen05_decode_consumer_restaged_sub_phases():
+    """The same with VLY_UMMA_XC=512: the activation block holds 512 columns, so down_proj (K = 3584) is walked in SEVEN sub-phases
+    with the block re-staged behind a CTA-local barrier and the accumulators resident in TMEM in between -- the mechanism the 13B
+    model uses for K = 13824 (3 pieces).  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
+            "print('ERR', t._decode_parity('tiny-umma', 4), t._decode_parity('tiny-umma', 2))") % (os.path.dirname(__file__), os.path.dirname(os.path.dirname(__file__)))
+    env = dict(os.environ, VLY_UMMA_XC="512")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "ERR" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

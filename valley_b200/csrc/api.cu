@@ -21,6 +21,7 @@
 #include "simt_kernels.cuh"
 #include "decode_kernels.cuh"
 #include "decode_mega.cuh"
+#include "decode_umma.cuh"
 #include "preprocess.cuh"
 #include "pooling_kernels.cuh"
 
@@ -162,6 +163,10 @@ struct vly_kv {
   long long* gen_tokens = nullptr;    // [B, Smax]
   int nsplit = 1, gemv_grid = 0;
   int stage_bytes = 0;                 // ring slot of the persistent decode kernel: max over its phases (pick_phase_geometry)
+  int n_grid_syncs = 0;                // grid barriers per decode launch
+  bool umma = false;                   // B = 2..4 on the tcgen05 consumer (decode_umma.cuh)
+  int umma_x_cols = 0;                 // columns of the swizzled activation block of that kernel
+  void* d_tmaps = nullptr;             // CUtensorMap[] of the weight matrices (one per phase geometry)
   PhaseDesc* d_phases = nullptr;
   int n_phases = 0;
   unsigned int* grid_counter = nullptr;
@@ -1250,10 +1255,15 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   CK(cudaEventCreateWithFlags(&kv->len_event, cudaEventDisableTiming));
   kv->d_step = kv->d_len + 1;
   CK(cudaMemset(kv->d_len, 0, 8));
-  CK(cudaMalloc((void**)&kv->x, (size_t)batch * H * 2));
-  CK(cudaMalloc((void**)&kv->q, (size_t)batch * H * 2));
-  CK(cudaMalloc((void**)&kv->attn, (size_t)batch * H * 2));
-  CK(cudaMalloc((void**)&kv->hb, (size_t)batch * I * 2));
+  // (8 rows tall, rows >= batch stay zero: the tcgen05 decode consumer stages these buffers as 8-row tensor-TMA boxes)
+  const size_t act_rows = batch < 8 ? 8 : batch;
+  CK(cudaMalloc((void**)&kv->x, act_rows * H * 2));
+  CK(cudaMalloc((void**)&kv->q, act_rows * H * 2));
+  CK(cudaMalloc((void**)&kv->attn, act_rows * H * 2));
+  CK(cudaMalloc((void**)&kv->hb, act_rows * I * 2));
+  CK(cudaMemset(kv->x, 0, act_rows * H * 2));
+  CK(cudaMemset(kv->attn, 0, act_rows * H * 2));
+  CK(cudaMemset(kv->hb, 0, act_rows * I * 2));
   CK(cudaMalloc((void**)&kv->part_o, (size_t)batch * nH * kv->nsplit * 128 * 4));
   CK(cudaMalloc((void**)&kv->part_ml, (size_t)batch * nH * kv->nsplit * sizeof(float2)));
   CK(cudaMalloc((void**)&kv->counters, ((size_t)batch * nH + 4) * 4));
@@ -1273,7 +1283,133 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   }
   CK(cudaMalloc((void**)&kv->key_bits, (size_t)batch * kv->mask_words() * 4));
   CK(cudaMemset(kv->key_bits, 0xff, (size_t)batch * kv->mask_words() * 4));
-  {  // phase table of the persistent decode-step kernel: execution order of one step
+  // ---- tcgen05 consumer for B = 2..4 (decode_umma.cuh): needs K multiples of 512 and the activation block + ring in 227 KB ----
+  {
+    static const int env_umma = getenv("VLY_DECODE_UMMA") ? atoi(getenv("VLY_DECODE_UMMA")) : 1;
+    static const int env_xc = getenv("VLY_UMMA_XC") ? atoi(getenv("VLY_UMMA_XC")) : 5120;      // (tests shrink it to force sub-phases)
+    const int bmax = batch <= 1 ? 1 : (batch <= 2 ? 2 : 4);
+    const int xcap = env_xc < H ? H : env_xc;
+    kv->umma = env_umma && bmax > 1 && batch <= 4 && decode_mode() == 2 && (H % 512 == 0) && (I % 512 == 0) && H <= 5120 && xcap % 512 == 0 &&
+               cdiv(cdiv(H, UmmaCfg::ROWS), c->num_sms) <= UmmaCfg::ACC_SLOTS;
+    if (kv->umma) {
+      // stage width: the largest multiple of 512 columns <= 2560 that divides K
+      auto kc_of = [](int K) {
+        for (int kc = 2560; kc >= 512; kc -= 512)
+          if (K % kc == 0) return kc;
+        return 512;
+      };
+      std::vector<PhaseDesc> ph;
+      std::vector<CUtensorMap> maps;
+      int err = VLY_OK;
+      auto add_map = [&](const bf16* W, int N, int K, int kc) -> int {       // -> index
+        CUtensorMap m;
+        cuuint64_t dims[3] = {64, (cuuint64_t)N, (cuuint64_t)(K / 64)};
+        cuuint64_t strides[2] = {(cuuint64_t)K * 2, 128};
+        cuuint32_t box[3] = {64, (cuuint32_t)UmmaCfg::ROWS, (cuuint32_t)(kc / 64)};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = c->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(W), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) err = fail(VLY_ERR_CUDA, "cuTensorMapEncodeTiled(decode weights, N=%d K=%d kc=%d) failed: %d", N, K, kc, (int)r);
+        maps.push_back(m);
+        return (int)maps.size() - 1;
+      };
+      static const int env_oob = getenv("VLY_UMMA_XOOB") ? atoi(getenv("VLY_UMMA_XOOB")) : 1;
+      auto add_xmap = [&](const bf16* X, int K, int x_cols) -> int {
+        CUtensorMap m;
+        // rows >= batch of the 8-row box lie outside the tensor: the TMA unit fills them with zeros without reading memory
+        cuuint64_t dims[3] = {64, (cuuint64_t)(env_oob ? batch : 8), (cuuint64_t)(K / 64)};
+        cuuint64_t strides[2] = {(cuuint64_t)K * 2, 128};
+        cuuint32_t box[3] = {64, 8, (cuuint32_t)(x_cols / 64)};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = c->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(X), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) err = fail(VLY_ERR_CUDA, "cuTensorMapEncodeTiled(decode activations, K=%d box %d) failed: %d", K, x_cols, (int)r);
+        maps.push_back(m);
+        return (int)maps.size() - 1;
+      };
+      std::vector<int> map_of;       // phase -> map index (-1: none)
+      std::vector<int> xmap_of;      // phase -> activation map index (-1: none)
+      int x_cols_max = 0, stage_max = 0, n_sync = 1;
+      // one weight matrix = one or more (sub-)phases: pieces of <= xcap columns (each staged once), a piece = full stages of kc
+      // columns plus, if kc does not divide it, ONE shorter tail stage per unit that re-uses the staged block
+      auto add_matrix = [&](PhaseDesc d, const bf16* W) {
+        const int K = d.K;
+        d.ldx = K; d.rows = UmmaCfg::ROWS;
+        int k0 = 0;
+        while (k0 < K) {
+          const int piece = (K - k0) < xcap ? (K - k0) : xcap;
+          int kc = kc_of(piece);
+          if (kc < 1536 && kc != piece) kc = piece < 2560 ? (piece / 512) * 512 : 2560;      // only small divisors: full stages + one tail stage
+          const int main_cols = (piece / kc) * kc, tail_cols = piece - main_cols;
+          const bool last_piece = (k0 + piece == K);
+          PhaseDesc q = d;
+          q.k_off = k0; q.K = main_cols; q.kc = kc; q.x_cols = piece; q.x_panel0 = 0;
+          q.flags = (k0 == 0 ? PHF_FIRST : 0);
+          if (tail_cols == 0) q.flags |= last_piece ? PHF_LAST : PHF_LOCAL_SYNC;
+          else q.flags |= PHF_NO_SYNC;
+          ph.push_back(q);
+          map_of.push_back(add_map(W, d.N, K, kc));
+          xmap_of.push_back(add_xmap(d.x_in, K, piece));
+          if (tail_cols > 0) {
+            PhaseDesc t = d;
+            t.k_off = k0 + main_cols; t.K = tail_cols; t.kc = tail_cols; t.x_cols = 0; t.x_panel0 = main_cols / 64;
+            t.flags = last_piece ? PHF_LAST : PHF_LOCAL_SYNC;
+            ph.push_back(t);
+            map_of.push_back(add_map(W, d.N, K, tail_cols));
+            xmap_of.push_back(-1);
+          }
+          if (piece > x_cols_max) x_cols_max = piece;
+          if (UmmaCfg::ROWS * kc * 2 > stage_max) stage_max = UmmaCfg::ROWS * kc * 2;
+          if (last_piece) ++n_sync;
+          k0 += piece;
+        }
+      };
+      for (int l = 0; l < L; ++l) {
+        const LlamaLayerW& w = c->layers[l];
+        PhaseDesc d = {};
+        d.layer = l; d.kcache = kv->k_layer(l); d.vcache = kv->v_layer(l);
+        d.type = PH_QKV; d.N = 3 * H; d.K = H; d.W = w.wqkv; d.x_in = kv->x; d.out = kv->q; add_matrix(d, w.wqkv);
+        d.type = PH_ATTN; d.N = 0; d.K = 0; d.W = nullptr; d.x_in = nullptr; d.out = kv->attn; ph.push_back(d); map_of.push_back(-1); xmap_of.push_back(-1); ++n_sync;
+        d.type = PH_OPROJ; d.N = H; d.K = H; d.W = w.wo; d.x_in = kv->attn; d.out = kv->x; add_matrix(d, w.wo);
+        d.type = PH_GATEUP; d.N = 2 * I; d.K = H; d.W = w.wgu; d.x_in = kv->x; d.out = kv->hb; add_matrix(d, w.wgu);
+        d.type = PH_DOWN; d.N = H; d.K = I; d.W = w.wdown; d.x_in = kv->hb; d.out = kv->x; add_matrix(d, w.wdown);
+      }
+      {
+        PhaseDesc d = {};
+        d.type = PH_LOGITS; d.N = V; d.K = H; d.W = c->lm_head; d.x_in = kv->x; d.out = nullptr; add_matrix(d, c->lm_head);
+      }
+      if (err != VLY_OK) return err;
+      static const int env_if = getenv("VLY_MEGA_INFLIGHT_KB") ? atoi(getenv("VLY_MEGA_INFLIGHT_KB")) : 100;
+      for (PhaseDesc& q : ph) {
+        if (q.type == PH_ATTN) continue;
+        const int sb = UmmaCfg::ROWS * q.kc * 2;
+        q.inflight = (env_if * 1024 + sb / 2) / sb;
+        if (q.inflight < 2) q.inflight = 2;
+      }
+      CK(cudaMalloc(&kv->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+      CK(cudaMemcpy(kv->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+      for (size_t i = 0; i < ph.size(); ++i)
+      {
+        ph[i].tmap = map_of[i] >= 0 ? (const void*)((const CUtensorMap*)kv->d_tmaps + map_of[i]) : nullptr;
+        ph[i].xmap = xmap_of[i] >= 0 ? (const void*)((const CUtensorMap*)kv->d_tmaps + xmap_of[i]) : nullptr;
+      }
+      kv->umma_x_cols = x_cols_max;
+      kv->stage_bytes = stage_max;
+      kv->n_grid_syncs = n_sync;
+      kv->n_phases = (int)ph.size();
+      if (getenv("VLY_MEGA_DBG")) {
+        fprintf(stderr, "[vly] decode (tcgen05 consumer): B=%d activation block %d columns (%d KB), stage %d B, %d phases (%d grid barriers);", batch,
+                x_cols_max, x_cols_max / 64, stage_max, kv->n_phases, n_sync);
+        for (int i = 0; i < 9 && i < (int)ph.size(); ++i)
+          if (ph[i].type != PH_ATTN)
+            fprintf(stderr, " [type%d N=%d k=%d+%d kc=%d stage_x=%d flags=%d]", ph[i].type, ph[i].N, ph[i].k_off, ph[i].K, ph[i].kc, ph[i].x_cols, ph[i].flags);
+        fprintf(stderr, "\n");
+      }
+      CK(cudaMalloc((void**)&kv->d_phases, ph.size() * sizeof(PhaseDesc)));
+      CK(cudaMemcpy(kv->d_phases, ph.data(), ph.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice));
+    }
+  }
+  if (!kv->umma) {  // phase table of the persistent decode-step kernel: execution order of one step
     std::vector<PhaseDesc> ph;
     const int bmax = batch <= 1 ? 1 : (batch <= 2 ? 2 : 4);
     const int pad = bmax > 1 ? MegaCfg::PAD_TC : 0;
@@ -1322,6 +1458,7 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
       fprintf(stderr, " logits rows=%d kc=%d\n", ph.back().rows, ph.back().kc);
     }
     kv->n_phases = (int)ph.size();
+    kv->n_grid_syncs = kv->n_phases + 1;
     CK(cudaMalloc((void**)&kv->d_phases, ph.size() * sizeof(PhaseDesc)));
     CK(cudaMemcpy(kv->d_phases, ph.data(), ph.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice));
   }
@@ -1336,7 +1473,7 @@ extern "C" void vly_kv_destroy(vly_kv* kv) {
   if (kv->graph_n) cudaGraphExecDestroy(kv->graph_n);
   if (kv->h_len) cudaFreeHost(kv->h_len);
   if (kv->len_event) cudaEventDestroy(kv->len_event);
-  void* ps[] = {kv->d_sample, kv->key_bits, kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
+  void* ps[] = {kv->d_tmaps, kv->d_sample, kv->key_bits, kv->dbg, kv->d_phases, kv->cache, kv->d_len, kv->x, kv->q, kv->attn, kv->hb, kv->part_o, kv->part_ml, kv->counters, kv->part_val, kv->part_idx, kv->logits, kv->cur_tokens, kv->gen_tokens};
   for (void* p : ps)
     if (p) cudaFree(p);
   delete kv;
@@ -1675,11 +1812,45 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   p.next_tokens = kv->cur_tokens; p.out_tokens = kv->gen_tokens; p.out_stride = kv->Smax;
   p.grid_counter = kv->grid_counter;
   p.grid_epoch = kv->grid_counter + 1;
+  p.n_grid_syncs = kv->n_grid_syncs;
+  {
+    static const int env_ik = getenv("VLY_ATTN_IKEYS") ? atoi(getenv("VLY_ATTN_IKEYS")) : 0;
+    p.attn_ikeys = (env_ik == 16 || env_ik == 32) ? env_ik : 0;
+  }
   p.sample = kv->d_sample;
   {
     static const bool want = getenv("VLY_MEGA_DBG") != nullptr;
     p.dbg = want ? kv->dbg : nullptr;
     g_mega_dbg = kv->dbg;
+  }
+  if (kv->umma) {
+    // tcgen05 consumer: swizzled activation block + ring of whole-box stages + barriers / handoff slots
+    p.Kmax = kv->umma_x_cols;
+    const size_t x_bytes = (size_t)(kv->umma_x_cols / 64) * 1024, stage_b = (size_t)kv->stage_bytes;
+    const size_t misc = ((1 + UmmaCfg::ISSUERS) * UmmaCfg::MAX_STAGES + 2 * UmmaCfg::ACC_SLOTS + 2 * UmmaCfg::RED_SLOTS + 2) * 8 + 16 +
+                        (size_t)UmmaCfg::RED_SLOTS * 4 * UmmaCfg::ROWS * bmax * 4 + (3 + 16) * bmax * 4 + 256;
+    int n_stages = (int)(((long long)227 * 1024 - 1024 - (long long)x_bytes - (long long)misc) / (long long)stage_b);
+    if (n_stages > UmmaCfg::MAX_STAGES) n_stages = UmmaCfg::MAX_STAGES;
+    static const int want = getenv("VLY_MEGA_STAGES") ? atoi(getenv("VLY_MEGA_STAGES")) : 0;
+    if (want > 0 && n_stages > want) n_stages = want;
+    if (n_stages < 2) return fail(VLY_ERR_INVALID, "decode (tcgen05 consumer): no room for the weight ring");
+    static const int inflight = getenv("VLY_MEGA_INFLIGHT") ? atoi(getenv("VLY_MEGA_INFLIGHT")) : 0;
+    p.n_stages = n_stages;
+    p.stage_bytes = (int)stage_b;
+    p.n_inflight = (inflight > 0 && inflight < n_stages) ? inflight : n_stages;
+    const size_t smem = x_bytes + (size_t)n_stages * stage_b + misc;
+    void* args[] = {&p};
+    cudaError_t e;
+    if (bmax == 2) {
+      TRY(ensure_smem_attr(c->cfg.device, decode_step_umma_kernel<2>, smem));
+      e = cudaLaunchCooperativeKernel((void*)decode_step_umma_kernel<2>, dim3(c->num_sms), dim3(MegaCfg::THREADS), args, smem, st);
+    } else {
+      TRY(ensure_smem_attr(c->cfg.device, decode_step_umma_kernel<4>, smem));
+      e = cudaLaunchCooperativeKernel((void*)decode_step_umma_kernel<4>, dim3(c->num_sms), dim3(MegaCfg::THREADS), args, smem, st);
+    }
+    c->launches++;
+    CK(e);
+    return VLY_OK;
   }
   size_t x_bytes, misc;
   mega_smem_layout(g, bmax, &x_bytes, &misc);

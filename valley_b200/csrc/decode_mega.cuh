@@ -29,12 +29,22 @@
 namespace vly {
 
 enum PhaseType : int { PH_QKV = 0, PH_ATTN = 1, PH_OPROJ = 2, PH_GATEUP = 3, PH_DOWN = 4, PH_LOGITS = 5 };
+enum PhaseFlags : int { PHF_FIRST = 1, PHF_LAST = 2, PHF_LOCAL_SYNC = 4, PHF_NO_SYNC = 8 };
 
 struct PhaseDesc {
   int type, N, K, layer;
   int rows, kc;                 // ring geometry of this phase: weight rows per work unit, columns per ring stage
-  int inflight;                 // stages of THIS phase's size kept in flight (~116 KB of bulk copies outstanding per SM)
+  int inflight;                 // stages of THIS phase's size kept in flight (~100 KB of bulk copies outstanding per SM)
+  // tcgen05 consumer (decode_umma.cuh) only: a weight matrix whose K does not fit the activation block is walked in sub-phases
+  int k_off;                    // first column of this (sub-)phase in the rows of W and of x_in
+  int ldx;                      // row stride of x_in in elements (the matrix's full K)
+  int x_cols;                   // columns of x_in staged at the start of this phase (0: the block staged by the previous sub-phase is reused)
+  int x_panel0;                 // 64-column panel of the staged block that holds column k_off
+  int flags;                    // PHF_FIRST: accumulators start from zero; PHF_LAST: the epilogue runs; PHF_LOCAL_SYNC: only this
+                                // CTA synchronises after it (the next sub-phase re-stages x), no grid barrier; PHF_NO_SYNC: none at all
   int pad_;
+  const void* tmap;             // CUtensorMap of W: dims {64, N, K/64}, box {64, 8, kc/64}
+  const void* xmap;             // CUtensorMap of x_in (8 rows tall, rows >= B zero): dims {64, 8, K/64}, box {64, 8, x_cols/64}
   const __nv_bfloat16* W;       // [N, K] (nullptr for PH_ATTN)
   const __nv_bfloat16* x_in;    // activation rows [B, K]
   __nv_bfloat16* out;           // QKV: q [B,H]; OPROJ/DOWN: x [B,H] (in place, also the residual); GATEUP: hb [B,I]
@@ -69,7 +79,9 @@ struct StepParams {
   int out_stride;
   SampleState* sample;          // token selection state (greedy / temperature sampling, eos bookkeeping); sampling.cuh
   unsigned int* grid_counter;   // monotonically increasing arrival counter of the grid barrier (never reset: no memset node per step)
-  unsigned int* grid_epoch;     // launches that ran to completion; barrier k of a launch waits for (epoch * n_barriers + k) * gridDim
+  unsigned int* grid_epoch;     // launches that ran to completion; barrier k of a launch waits for (epoch * n_grid_syncs + k) * gridDim
+  int n_grid_syncs;             // grid barriers one launch executes (one per grid-synchronised phase + the embedding phase)
+  int attn_ikeys;               // 0: pick 16 / 32 keys per attention item by shape; else forced (VLY_ATTN_IKEYS, A/B measurements)
   int n_stages;
   int stage_bytes;              // ring slot size: max over the phases of rows * (kc * 2 + row pad)
   int n_inflight;               // global cap on the stages in flight (PhaseDesc::inflight is the per-phase value; the ring may be deeper)
@@ -124,6 +136,284 @@ VLY_DEVINL void grid_sync_consumers(unsigned int* counter, unsigned int target, 
     }
   }
   asm volatile("bar.sync 2, 544;" ::: "memory");
+}
+
+// ------------------------------ attention phase (shared by both step kernels) ------------------------------
+// Runs on the 16 compute warps (cw = 0..15); no block-level barrier inside.
+// ------------------------------ attention phase (shared by both step kernels) ------------------------------
+// Runs on the 16 compute warps (cw = 0..15); no block-level barrier inside.
+// (A CTA-per-(sequence, head) variant with a shared-memory merge was measured at 13B, B = 4: slower -- one SM cannot keep enough
+//  K/V loads in flight from registers; spreading every head over all SMs wins despite the global-memory merge.)
+VLY_DEVINL void mega_attention_phase(const StepParams& p, const PhaseDesc& d, const int cw, const int lane, const int pos) {
+  // ------------------------------ attention: one warp per (sequence, head, 32-key split) ------------------------------
+  // A half-warp covers one key row (16 lanes x 16 bytes = 128 head dims); a pass handles 16 keys (8 per half-warp): all 8 K
+  // and 8 V rows of a lane are requested up front (one L2 / HBM round trip), scores are reduced with a transposing shuffle
+  // tree (8 instead of 32 shuffles), softmax runs online in registers across the two passes of an item, P.V accumulates per
+  // lane over its 8 head dims.  Items are dealt warp-major over the SMs so one layer's K/V is pulled by every SM at once.
+  // Item size: with few (sequence, head, 16-key) items -- short contexts, B = 1 -- every item gets its own warp and a single
+  // round trip to the cache; otherwise 32 keys per item (two passes) halve the partials the merge has to read.
+  const int len = pos + 1;
+  // (the phase lasts as long as its busiest warp: rounds x keys per item -- e.g. 2400 32-key items on 2368 warps are 2 rounds of
+  //  32 keys, the same work as 4800 16-key items are 3 rounds of 16)
+  const int n_warps = 16 * (int)gridDim.x;
+  const int it16 = p.B * p.nH * ((len + 15) >> 4), it32 = p.B * p.nH * ((len + 31) >> 5);
+  const int w16 = ((it16 + n_warps - 1) / n_warps) * 16, w32 = ((it32 + n_warps - 1) / n_warps) * 32;
+  const int ikeys = p.attn_ikeys ? p.attn_ikeys : ((w16 < w32 || (w16 == w32 && it16 <= n_warps)) ? 16 : 32);   // tie: one pass if everything fits one round
+  const int n_act = (len + ikeys - 1) / ikeys;
+  const int items = p.B * p.nH * n_act;
+  const int hl = lane & 15, hw = lane >> 4;
+  for (int it = cw * gridDim.x + blockIdx.x; it < items; it += gridDim.x * 16) {
+    const int split = it % n_act, bh = it / n_act;
+    const int b = bh / p.nH, h = bh - b * p.nH;
+    const int k0 = split * ikeys, nk = min(len - k0, ikeys);
+    const __nv_bfloat16* kb = d.kcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
+    const __nv_bfloat16* vb = d.vcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
+    const uint32_t kbits = __ldg(p.key_bits + (size_t)b * p.mask_words + (k0 >> 5)) >> (k0 & 31);   // one mask bit per cache position
+    float qf[8];
+    {
+      const uint4 w = ldcg_v4(p.q + (size_t)b * p.H + h * 128 + hl * 8);
+      qf[0] = bf16_lo(w.x); qf[1] = bf16_hi(w.x); qf[2] = bf16_lo(w.y); qf[3] = bf16_hi(w.y);
+      qf[4] = bf16_lo(w.z); qf[5] = bf16_hi(w.z); qf[6] = bf16_lo(w.w); qf[7] = bf16_hi(w.w);
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int kk0 = 0; kk0 < nk; kk0 += 16) {
+      uint4 kw[8], vw[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int key = kk0 + 2 * j + hw;
+        const bool ok = key < nk;
+        kw[j] = ok ? ldcg_v4(kb + (size_t)key * 128) : make_uint4(0, 0, 0, 0);
+        vw[j] = ok ? ldcg_v4(vb + (size_t)key * 128) : make_uint4(0, 0, 0, 0);
+      }
+      float sc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 w = kw[j];
+        sc[j] = qf[0] * bf16_lo(w.x) + qf[1] * bf16_hi(w.x) + qf[2] * bf16_lo(w.y) + qf[3] * bf16_hi(w.y) +
+                qf[4] * bf16_lo(w.z) + qf[5] * bf16_hi(w.z) + qf[6] * bf16_lo(w.w) + qf[7] * bf16_hi(w.w);
+      }
+      // transposing reduction over the 16 lanes of the half-warp: afterwards sc[0] = the full dot product of key
+      // kk0 + 2 * (hl >> 1) + hw (held twice: lanes hl and hl ^ 1)
+#pragma unroll
+      for (int off = 8, n = 4; off >= 2; off >>= 1, n >>= 1) {
+        const bool up = (hl & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < n) {
+            const float send = up ? sc[i] : sc[i + n];
+            const float keep = up ? sc[i + n] : sc[i];
+            sc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+      }
+      sc[0] += __shfl_xor_sync(0xffffffffu, sc[0], 1);
+      const int my_key = kk0 + 2 * (hl >> 1) + hw;
+      const bool valid = my_key < nk && ((kbits >> my_key) & 1u);
+      const float s_my = valid ? sc[0] * p.scale_log2e : -INFINITY;
+      float mx = s_my;
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+      const float m_new = fmaxf(m_run, mx);
+      const float pm = valid ? fast_exp2(s_my - m_new) : 0.f;              // (valid => m_new is finite)
+      const float corr = (m_run > -INFINITY) ? fast_exp2(m_run - m_new) : 0.f;
+      float ls = pm;                                                         // every key is held by a lane pair: skip xor 1
+      ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 4);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 8);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 16);
+      l_run = l_run * corr + ls;
+      m_run = m_new;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] *= corr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, pm, (lane & 16) + 2 * j);  // weight of key kk0 + 2j + hw
+        const uint4 w = vw[j];
+        o[0] = fmaf(pj, bf16_lo(w.x), o[0]); o[1] = fmaf(pj, bf16_hi(w.x), o[1]);
+        o[2] = fmaf(pj, bf16_lo(w.y), o[2]); o[3] = fmaf(pj, bf16_hi(w.y), o[3]);
+        o[4] = fmaf(pj, bf16_lo(w.z), o[4]); o[5] = fmaf(pj, bf16_hi(w.z), o[5]);
+        o[6] = fmaf(pj, bf16_lo(w.w), o[6]); o[7] = fmaf(pj, bf16_hi(w.w), o[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);   // even + odd keys
+    if (n_act == 1) {
+      // the whole (sequence, head) fitted one item: no partials, no merge
+      if (hw == 0) {
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        *reinterpret_cast<uint4*>(p.attn + (size_t)b * p.H + h * 128 + hl * 8) =
+            make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
+                       pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
+      }
+      continue;
+    }
+    float* po = p.part_o + ((size_t)bh * p.nsplit + split) * 128 + hl * 8;
+    if (hw == 0) {
+      *reinterpret_cast<float4*>(po) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(po + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (lane == 0) p.part_ml[(size_t)bh * p.nsplit + split] = make_float2(m_run, l_run);
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(p.attn_counters + bh, 1u) == (unsigned)n_act - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      // ---- merge of the n_act (<= 128) partials by the warp that arrived last: lane s holds (max, sum) of splits s + 32 i.
+      // The first batch of partial outputs is requested together with the (max, sum) pairs: one L2 round trip, not two.
+      __threadfence();
+      const float* pb = p.part_o + (size_t)bh * p.nsplit * 128 + lane * 4;
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = (j < n_act) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float mv[4], lv[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        mv[i] = -INFINITY;
+        lv[i] = 0.f;
+        if (lane + 32 * i < n_act) {
+          const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane + 32 * i]);
+          mv[i] = ml.x;
+          lv[i] = ml.y;
+        }
+      }
+      const float Mx = warp_max(fmaxf(fmaxf(mv[0], mv[1]), fmaxf(mv[2], mv[3])));
+      float lw = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        wv[i] = lv[i] > 0.f ? fast_exp2(mv[i] - Mx) : 0.f;                  // a fully masked split has m = -inf, l = 0
+        lw += lv[i] * wv[i];
+      }
+      const float L = warp_sum(lw);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s0 = 0; s0 < n_act; s0 += 8) {
+        const int gi = s0 >> 5;
+        const float wsel = gi == 0 ? wv[0] : (gi == 1 ? wv[1] : (gi == 2 ? wv[2] : wv[3]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float w = __shfl_sync(0xffffffffu, wsel, (s0 + j) & 31);
+          acc.x = fmaf(v[j].x, w, acc.x); acc.y = fmaf(v[j].y, w, acc.y);
+          acc.z = fmaf(v[j].z, w, acc.z); acc.w = fmaf(v[j].w, w, acc.w);
+        }
+        if (s0 + 8 < n_act) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[j] = (s0 + 8 + j < n_act) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)(s0 + 8 + j) * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      const float inv = L > 0.f ? 1.f / L : 0.f;
+      *reinterpret_cast<uint2*>(p.attn + (size_t)b * p.H + h * 128 + lane * 4) =
+          make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
+      if (lane == 0) p.attn_counters[bh] = 0;
+    }
+  }
+}
+
+// operands of the epilogue that do not depend on the unit's result: fetched while the unit is still being computed
+VLY_DEVINL void mega_epilogue_prefetch(const StepParams& p, const PhaseDesc& d, const bool ok, const int b, const int n, const int pos,
+                                       float& pre0, float& pre1) {
+  if (ok) {
+    if (d.type == PH_OPROJ || d.type == PH_DOWN) pre0 = ldcg_bf16(d.out + (size_t)b * d.N + n);
+    else if (d.type == PH_QKV && n < 2 * p.H) {
+      const float2 cs = __ldg(p.rope + (size_t)pos * 64 + ((n & 127) >> 1));
+      pre0 = cs.x;
+      pre1 = cs.y;
+    }
+  }
+}
+
+// ------------------------------ fused epilogue of one work unit (shared by both step kernels) ------------------------------
+// Executed by the lanes < NV of the epilogue warp: lane = r * BMAX + b holds t = the finished dot product of weight row n = n0 + r
+// and batch row b.  pre0 / pre1: the operand prefetched before the unit completed (residual, or RoPE cos / sin).
+template <int BMAX, int NV>
+VLY_DEVINL void mega_unit_epilogue(const StepParams& p, const PhaseDesc& d, const int lane, const float t, const bool ok, const int r,
+                                   const int b, const int n, const float pre0, const float pre1, const int pos, const float* rstd_s,
+                                   float* bestv, int* besti, const bool samp_on, const float samp_it, const uint32_t samp_k0,
+                                   const uint32_t samp_k1) {
+  constexpr unsigned kMask = (NV == 32) ? 0xffffffffu : ((1u << NV) - 1u);
+  if (d.type == PH_OPROJ || d.type == PH_DOWN) {
+    if (ok) d.out[(size_t)b * d.N + n] = __float2bfloat16_rn(t + pre0);
+  } else if (d.type == PH_LOGITS) {
+    const float y = t * rstd_s[b];
+    if (ok && p.logits != nullptr) p.logits[(size_t)b * d.N + n] = y;
+    // greedy: the logit itself; sampling: logit / T + Gumbel noise (arg-max == multinomial(softmax(logits / T)))
+    float bv = ok ? (samp_on ? sample_score(y, samp_it, samp_k0, samp_k1, n, b, pos) : y) : -INFINITY;
+    int bi = n;
+#pragma unroll
+    for (int o = BMAX; o < NV; o <<= 1) {
+      const float ov = __shfl_xor_sync(kMask, bv, o);
+      const int oi = __shfl_xor_sync(kMask, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane < BMAX && lane < p.B && bv > bestv[lane]) {
+      bestv[lane] = bv;
+      besti[lane] = bi;
+    }
+  } else {
+    const float mine = t * rstd_s[b];
+    const float other = __shfl_xor_sync(kMask, mine, BMAX);
+    if ((r & 1) == 0 && ok && n + 1 < d.N) {
+      float x0 = mine, x1 = other;
+      if (d.type == PH_GATEUP) {
+        const float gte = bf16_round(x0), up = bf16_round(x1);      // HF:modeling_llama.py:182-184 rounds both
+        d.out[(size_t)b * (d.N >> 1) + (n >> 1)] = __float2bfloat16_rn(bf16_round(gte / (1.f + __expf(-gte))) * up);
+      } else {
+        const int which = n / p.H, nh = n - which * p.H, head = nh >> 7, cidx = nh & 127;
+        if (which < 2) {
+          const float a = x0 * pre0 - x1 * pre1, c2 = x1 * pre0 + x0 * pre1;   // (cos, sin) prefetched
+          x0 = a;
+          x1 = c2;
+        }
+        __nv_bfloat16* dst;
+        if (which == 0) dst = d.out + (size_t)b * p.H + nh;
+        else dst = ((which == 1) ? d.kcache : d.vcache) + (((size_t)b * p.nH + head) * p.Smax + pos) * 128 + cidx;
+        *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x0, x1);
+      }
+    }
+  }
+}
+
+// ---- greedy arg-max over the per-CTA partials (lowest index on ties, like torch.argmax); advance the counters.
+// Executed by the 16 compute warps of CTA 0 after the last grid barrier of the step. ----
+VLY_DEVINL void mega_finish_step(const StepParams& p, const int cw, const int lane, const int ct) {
+      if (cw < p.B) {
+        const int b = cw;
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int g = lane; g < (int)gridDim.x; g += 32) {
+          const float v = __ldcg(p.part_val + (size_t)b * gridDim.x + g);
+          const int i = __ldcg(p.part_idx + (size_t)b * gridDim.x + g);
+          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+  #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+          const long long tok = sample_finish_row(p.sample, b, bi);
+          p.next_tokens[b] = tok;
+          if (p.out_tokens != nullptr) p.out_tokens[(size_t)b * p.out_stride + *p.step] = tok;
+        }
+      }
+      asm volatile("bar.sync 7, 512;" ::: "memory");
+      if (ct == 0) {
+        *p.step += 1;
+        *p.seq_len += 1;
+        *p.grid_epoch += 1;          // every CTA has passed the last barrier of this launch (they read the epoch at their start)
+        p.sample->steps_valid += 1;
+        if (p.sample->eos >= 0 || p.sample->stop2 >= 0) {
+          int all = 1;
+          for (int b = 0; b < p.B; ++b) all &= p.sample->done[b];
+          p.sample->all_done = all;
+        }
+      }
 }
 
 template <int BMAX>
@@ -226,7 +516,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
   const uint32_t samp_k0 = p.sample->seed_lo, samp_k1 = p.sample->seed_hi;
   unsigned int sync_no = 0;
   // written by block 0 at the very end of the previous completed launch (stream order): the same value in every CTA
-  const unsigned int sync_base = *p.grid_epoch * (unsigned int)(p.n_phases + 1) * gridDim.x;
+  const unsigned int sync_base = *p.grid_epoch * (unsigned int)p.n_grid_syncs * gridDim.x;
   long long t_sync = 0, t_stage = 0, t_loop = 0, t_attn = 0, t0 = clock64();
   long long* dbg_o = (p.dbg != nullptr && ct == 0) ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
   if (dbg_o != nullptr)
@@ -257,170 +547,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
     // (an L1 prefetch of the next descriptor was tried here: it made every grid barrier ~1 us SLOWER -- bisected on the GPU)
     t0 = clock64();
     if (d.type == PH_ATTN) {
-      if (!is_fin) {
-        // ------------------------------ attention: one warp per (sequence, head, 32-key split) ------------------------------
-        // A half-warp covers one key row (16 lanes x 16 bytes = 128 head dims); a pass handles 16 keys (8 per half-warp): all 8 K
-        // and 8 V rows of a lane are requested up front (one L2 / HBM round trip), scores are reduced with a transposing shuffle
-        // tree (8 instead of 32 shuffles), softmax runs online in registers across the two passes of an item, P.V accumulates per
-        // lane over its 8 head dims.  Items are dealt warp-major over the SMs so one layer's K/V is pulled by every SM at once.
-        // Item size: with few (sequence, head, 16-key) items -- short contexts, B = 1 -- every item gets its own warp and a single
-        // round trip to the cache; otherwise 32 keys per item (two passes) halve the partials the merge has to read.
-        const int len = pos + 1;
-        const int ikeys = (p.B * p.nH * ((len + 15) >> 4) <= 16 * (int)gridDim.x) ? 16 : 32;
-        const int n_act = (len + ikeys - 1) / ikeys;
-        const int items = p.B * p.nH * n_act;
-        const int hl = lane & 15, hw = lane >> 4;
-        for (int it = cw * gridDim.x + blockIdx.x; it < items; it += gridDim.x * 16) {
-          const int split = it % n_act, bh = it / n_act;
-          const int b = bh / p.nH, h = bh - b * p.nH;
-          const int k0 = split * ikeys, nk = min(len - k0, ikeys);
-          const __nv_bfloat16* kb = d.kcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
-          const __nv_bfloat16* vb = d.vcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
-          const uint32_t kbits = __ldg(p.key_bits + (size_t)b * p.mask_words + (k0 >> 5)) >> (k0 & 31);   // one mask bit per cache position
-          float qf[8];
-          {
-            const uint4 w = ldcg_v4(p.q + (size_t)b * p.H + h * 128 + hl * 8);
-            qf[0] = bf16_lo(w.x); qf[1] = bf16_hi(w.x); qf[2] = bf16_lo(w.y); qf[3] = bf16_hi(w.y);
-            qf[4] = bf16_lo(w.z); qf[5] = bf16_hi(w.z); qf[6] = bf16_lo(w.w); qf[7] = bf16_hi(w.w);
-          }
-          float m_run = -INFINITY, l_run = 0.f;
-          float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int kk0 = 0; kk0 < nk; kk0 += 16) {
-            uint4 kw[8], vw[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int key = kk0 + 2 * j + hw;
-              const bool ok = key < nk;
-              kw[j] = ok ? ldcg_v4(kb + (size_t)key * 128) : make_uint4(0, 0, 0, 0);
-              vw[j] = ok ? ldcg_v4(vb + (size_t)key * 128) : make_uint4(0, 0, 0, 0);
-            }
-            float sc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 w = kw[j];
-              sc[j] = qf[0] * bf16_lo(w.x) + qf[1] * bf16_hi(w.x) + qf[2] * bf16_lo(w.y) + qf[3] * bf16_hi(w.y) +
-                      qf[4] * bf16_lo(w.z) + qf[5] * bf16_hi(w.z) + qf[6] * bf16_lo(w.w) + qf[7] * bf16_hi(w.w);
-            }
-            // transposing reduction over the 16 lanes of the half-warp: afterwards sc[0] = the full dot product of key
-            // kk0 + 2 * (hl >> 1) + hw (held twice: lanes hl and hl ^ 1)
-#pragma unroll
-            for (int off = 8, n = 4; off >= 2; off >>= 1, n >>= 1) {
-              const bool up = (hl & off) != 0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (i < n) {
-                  const float send = up ? sc[i] : sc[i + n];
-                  const float keep = up ? sc[i + n] : sc[i];
-                  sc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-              }
-            }
-            sc[0] += __shfl_xor_sync(0xffffffffu, sc[0], 1);
-            const int my_key = kk0 + 2 * (hl >> 1) + hw;
-            const bool valid = my_key < nk && ((kbits >> my_key) & 1u);
-            const float s_my = valid ? sc[0] * p.scale_log2e : -INFINITY;
-            float mx = s_my;
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-            const float m_new = fmaxf(m_run, mx);
-            const float pm = valid ? fast_exp2(s_my - m_new) : 0.f;              // (valid => m_new is finite)
-            const float corr = (m_run > -INFINITY) ? fast_exp2(m_run - m_new) : 0.f;
-            float ls = pm;                                                         // every key is held by a lane pair: skip xor 1
-            ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-            ls += __shfl_xor_sync(0xffffffffu, ls, 4);
-            ls += __shfl_xor_sync(0xffffffffu, ls, 8);
-            ls += __shfl_xor_sync(0xffffffffu, ls, 16);
-            l_run = l_run * corr + ls;
-            m_run = m_new;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] *= corr;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float pj = __shfl_sync(0xffffffffu, pm, (lane & 16) + 2 * j);  // weight of key kk0 + 2j + hw
-              const uint4 w = vw[j];
-              o[0] = fmaf(pj, bf16_lo(w.x), o[0]); o[1] = fmaf(pj, bf16_hi(w.x), o[1]);
-              o[2] = fmaf(pj, bf16_lo(w.y), o[2]); o[3] = fmaf(pj, bf16_hi(w.y), o[3]);
-              o[4] = fmaf(pj, bf16_lo(w.z), o[4]); o[5] = fmaf(pj, bf16_hi(w.z), o[5]);
-              o[6] = fmaf(pj, bf16_lo(w.w), o[6]); o[7] = fmaf(pj, bf16_hi(w.w), o[7]);
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);   // even + odd keys
-          if (n_act == 1) {
-            // the whole (sequence, head) fitted one item: no partials, no merge
-            if (hw == 0) {
-              const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-              *reinterpret_cast<uint4*>(p.attn + (size_t)b * p.H + h * 128 + hl * 8) =
-                  make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
-                             pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
-            }
-            continue;
-          }
-          float* po = p.part_o + ((size_t)bh * p.nsplit + split) * 128 + hl * 8;
-          if (hw == 0) {
-            *reinterpret_cast<float4*>(po) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(po + 4) = make_float4(o[4], o[5], o[6], o[7]);
-          }
-          if (lane == 0) p.part_ml[(size_t)bh * p.nsplit + split] = make_float2(m_run, l_run);
-          __threadfence();
-          __syncwarp();
-          int last = 0;
-          if (lane == 0) last = (atomicAdd(p.attn_counters + bh, 1u) == (unsigned)n_act - 1);
-          last = __shfl_sync(0xffffffffu, last, 0);
-          if (last) {
-            // ---- merge of the n_act (<= 128) partials by the warp that arrived last: lane s holds (max, sum) of splits s + 32 i.
-            // The first batch of partial outputs is requested together with the (max, sum) pairs: one L2 round trip, not two.
-            __threadfence();
-            const float* pb = p.part_o + (size_t)bh * p.nsplit * 128 + lane * 4;
-            float4 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              v[j] = (j < n_act) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float mv[4], lv[4], wv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              mv[i] = -INFINITY;
-              lv[i] = 0.f;
-              if (lane + 32 * i < n_act) {
-                const float2 ml = __ldcg(&p.part_ml[(size_t)bh * p.nsplit + lane + 32 * i]);
-                mv[i] = ml.x;
-                lv[i] = ml.y;
-              }
-            }
-            const float Mx = warp_max(fmaxf(fmaxf(mv[0], mv[1]), fmaxf(mv[2], mv[3])));
-            float lw = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              wv[i] = lv[i] > 0.f ? fast_exp2(mv[i] - Mx) : 0.f;                  // a fully masked split has m = -inf, l = 0
-              lw += lv[i] * wv[i];
-            }
-            const float L = warp_sum(lw);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s0 = 0; s0 < n_act; s0 += 8) {
-              const int gi = s0 >> 5;
-              const float wsel = gi == 0 ? wv[0] : (gi == 1 ? wv[1] : (gi == 2 ? wv[2] : wv[3]));
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float w = __shfl_sync(0xffffffffu, wsel, (s0 + j) & 31);
-                acc.x = fmaf(v[j].x, w, acc.x); acc.y = fmaf(v[j].y, w, acc.y);
-                acc.z = fmaf(v[j].z, w, acc.z); acc.w = fmaf(v[j].w, w, acc.w);
-              }
-              if (s0 + 8 < n_act) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  v[j] = (s0 + 8 + j < n_act) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)(s0 + 8 + j) * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
-            const float inv = L > 0.f ? 1.f / L : 0.f;
-            *reinterpret_cast<uint2*>(p.attn + (size_t)b * p.H + h * 128 + lane * 4) =
-                make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
-            if (lane == 0) p.attn_counters[bh] = 0;
-          }
-        }
-      }
+      if (!is_fin) mega_attention_phase(p, d, cw, lane, pos);
       t_attn += clock64() - t0;
       if (dbg_o != nullptr) dbg_o[8 + 3 * PH_ATTN + 1] += clock64() - t0;
     } else {
@@ -569,7 +696,6 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
         }
       } else {
         // ===== finalize warp: sum the 16 partials of each unit, fused epilogue =====
-        constexpr unsigned kMask = (NV == 32) ? 0xffffffffu : ((1u << NV) - 1u);
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++unit_no) {
           const int n0 = g * rows_u;
           const int slot = unit_no & (M::RED_SLOTS - 1);
@@ -578,14 +704,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
           const bool ok = lane < NV && r < rows_u && b < p.B && n < d.N;
           // operands of the epilogue are fetched while the compute warps are still busy with this unit
           float pre0 = 0.f, pre1 = 0.f;
-          if (ok) {
-            if (d.type == PH_OPROJ || d.type == PH_DOWN) pre0 = ldcg_bf16(d.out + (size_t)b * d.N + n);
-            else if (d.type == PH_QKV && n < 2 * p.H) {
-              const float2 cs = __ldg(p.rope + (size_t)pos * 64 + ((n & 127) >> 1));
-              pre0 = cs.x;
-              pre1 = cs.y;
-            }
-          }
+          mega_epilogue_prefetch(p, d, ok, b, n, pos, pre0, pre1);
           mbar_wait(&red_full[slot], round);
           float t = 0.f;
           if (lane < NV) {
@@ -594,48 +713,8 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&red_empty[slot]);
-          if (lane < NV) {
-            if (d.type == PH_OPROJ || d.type == PH_DOWN) {
-              if (ok) d.out[(size_t)b * d.N + n] = __float2bfloat16_rn(t + pre0);
-            } else if (d.type == PH_LOGITS) {
-              const float y = t * rstd_s[b];
-              if (ok && p.logits != nullptr) p.logits[(size_t)b * d.N + n] = y;
-              // greedy: the logit itself; sampling: logit / T + Gumbel noise (arg-max == multinomial(softmax(logits / T)))
-              float bv = ok ? (samp_on ? sample_score(y, samp_it, samp_k0, samp_k1, n, b, pos) : y) : -INFINITY;
-              int bi = n;
-#pragma unroll
-              for (int o = BMAX; o < NV; o <<= 1) {
-                const float ov = __shfl_xor_sync(kMask, bv, o);
-                const int oi = __shfl_xor_sync(kMask, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-              }
-              if (lane < BMAX && lane < p.B && bv > bestv[lane]) {
-                bestv[lane] = bv;
-                besti[lane] = bi;
-              }
-            } else {
-              const float mine = t * rstd_s[b];
-              const float other = __shfl_xor_sync(kMask, mine, BMAX);
-              if ((r & 1) == 0 && ok && n + 1 < d.N) {
-                float x0 = mine, x1 = other;
-                if (d.type == PH_GATEUP) {
-                  const float gte = bf16_round(x0), up = bf16_round(x1);      // HF:modeling_llama.py:182-184 rounds both
-                  d.out[(size_t)b * (d.N >> 1) + (n >> 1)] = __float2bfloat16_rn(bf16_round(gte / (1.f + __expf(-gte))) * up);
-                } else {
-                  const int which = n / p.H, nh = n - which * p.H, head = nh >> 7, cidx = nh & 127;
-                  if (which < 2) {
-                    const float a = x0 * pre0 - x1 * pre1, c2 = x1 * pre0 + x0 * pre1;   // (cos, sin) prefetched
-                    x0 = a;
-                    x1 = c2;
-                  }
-                  __nv_bfloat16* dst;
-                  if (which == 0) dst = d.out + (size_t)b * p.H + nh;
-                  else dst = ((which == 1) ? d.kcache : d.vcache) + (((size_t)b * p.nH + head) * p.Smax + pos) * 128 + cidx;
-                  *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x0, x1);
-                }
-              }
-            }
-          }
+          if (lane < NV)
+            mega_unit_epilogue<BMAX, NV>(p, d, lane, t, ok, r, b, n, pre0, pre1, pos, rstd_s, bestv, besti, samp_on, samp_it, samp_k0, samp_k1);
         }
       }
       t_loop += clock64() - t0;
@@ -654,42 +733,7 @@ __global__ void __launch_bounds__(576, 1) decode_step_kernel(const StepParams p)
     dbg_o[0] = t_sync; dbg_o[1] = t_stage; dbg_o[2] = t_loop; dbg_o[3] = t_attn; dbg_o[4] = 0;
   }
 
-  // ---- greedy arg-max over the per-CTA partials (lowest index on ties, like torch.argmax); advance the counters ----
-  if (blockIdx.x == 0 && !is_fin) {
-    if (cw < p.B) {
-      const int b = cw;
-      float bv = -INFINITY;
-      int bi = 0x7fffffff;
-      for (int g = lane; g < (int)gridDim.x; g += 32) {
-        const float v = __ldcg(p.part_val + (size_t)b * gridDim.x + g);
-        const int i = __ldcg(p.part_idx + (size_t)b * gridDim.x + g);
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (lane == 0) {
-        const long long tok = sample_finish_row(p.sample, b, bi);
-        p.next_tokens[b] = tok;
-        if (p.out_tokens != nullptr) p.out_tokens[(size_t)b * p.out_stride + *p.step] = tok;
-      }
-    }
-    asm volatile("bar.sync 7, 512;" ::: "memory");
-    if (ct == 0) {
-      *p.step += 1;
-      *p.seq_len += 1;
-      *p.grid_epoch += 1;          // every CTA has passed the last barrier of this launch (they read the epoch at their start)
-      p.sample->steps_valid += 1;
-      if (p.sample->eos >= 0 || p.sample->stop2 >= 0) {
-        int all = 1;
-        for (int b = 0; b < p.B; ++b) all &= p.sample->done[b];
-        p.sample->all_done = all;
-      }
-    }
-  }
+  if (blockIdx.x == 0 && !is_fin) mega_finish_step(p, cw, lane, ct);
 }
 
 }  // namespace vly
