@@ -748,14 +748,24 @@ def test_tcgen05_decode_consumer_full_and_tail_stages(B):
     _decode_parity("tiny-umma", B)
 
 
+def _decode_parity_subprocess(env, calls):
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; print('ERR', %s)"
+            % (os.path.dirname(__file__), os.path.dirname(os.path.dirname(__file__)), ", ".join("t._decode_parity(%r, %d)" % c for c in calls)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+    assert r.returncode == 0 and "ERR" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_tcgen05_decode_consumer_ragged_k():
+    """intermediate_size = 3776 = 59 panels of 64 columns (Llama-2-7B: 11008 = 172): the K walk is rounded up to whole 512-column
+    groups and the panels beyond the real K are out of bounds in both tensor maps (zero fill, no memory read).  Not the default for
+    such shapes (measured slower than the mma.sync consumer on Llama-2-7B), so it is forced with VLY_DECODE_UMMA=2."""
+    _decode_parity_subprocess({"VLY_DECODE_UMMA": "2"}, [("tiny-umma-ragged", 2), ("tiny-umma-ragged", 4)])
+
+
 def test_tcgen05_decode_consumer_restaged_sub_phases():
     """The same with VLY_UMMA_XC=512: the activation block holds 512 columns, so down_proj (K = 3584) is walked in SEVEN sub-phases
     with the block re-staged behind a CTA-local barrier and the accumulators resident in TMEM in between -- the mechanism the 13B
     model uses for K = 13824 (3 pieces).  The switch is read once per process, hence the subprocess."""
-    import subprocess
-    import sys
-    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
-            "print('ERR', t._decode_parity('tiny-umma', 4), t._decode_parity('tiny-umma', 2))") % (os.path.dirname(__file__), os.path.dirname(os.path.dirname(__file__)))
-    env = dict(os.environ, VLY_UMMA_XC="512")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
-    assert r.returncode == 0 and "ERR" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    _decode_parity_subprocess({"VLY_UMMA_XC": "512"}, [("tiny-umma", 4), ("tiny-umma", 2)])

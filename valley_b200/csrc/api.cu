@@ -1283,13 +1283,16 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   }
   CK(cudaMalloc((void**)&kv->key_bits, (size_t)batch * kv->mask_words() * 4));
   CK(cudaMemset(kv->key_bits, 0xff, (size_t)batch * kv->mask_words() * 4));
-  // ---- tcgen05 consumer for B = 2..4 (decode_umma.cuh): needs K multiples of 512 and the activation block + ring in 227 KB ----
+  // ---- tcgen05 consumer for B = 2..4 (decode_umma.cuh): needs H a multiple of 512, I of 64, and the activation block + ring in 227 KB ----
   {
     static const int env_umma = getenv("VLY_DECODE_UMMA") ? atoi(getenv("VLY_DECODE_UMMA")) : 1;
     static const int env_xc = getenv("VLY_UMMA_XC") ? atoi(getenv("VLY_UMMA_XC")) : 5120;      // (tests shrink it to force sub-phases)
     const int bmax = batch <= 1 ? 1 : (batch <= 2 ? 2 : 4);
     const int xcap = env_xc < H ? H : env_xc;
-    kv->umma = env_umma && bmax > 1 && batch <= 4 && decode_mode() == 2 && (H % 512 == 0) && (I % 512 == 0) && H <= 5120 && xcap % 512 == 0 &&
+    // (I not a multiple of 512 -- Llama-2-7B's 11008 -- works through zero-filled out-of-bounds panels but measured slower than the
+    //  mma.sync consumer there: 3.82 vs 3.58 ms/step at B = 4, three activation re-stagings for down_proj; VLY_DECODE_UMMA=2 forces it)
+    kv->umma = env_umma && bmax > 1 && batch <= 4 && decode_mode() == 2 && (H % 512 == 0) && (I % 512 == 0 || (env_umma >= 2 && I % 64 == 0)) &&
+               H <= 5120 && xcap % 512 == 0 &&
                cdiv(cdiv(H, UmmaCfg::ROWS), c->num_sms) <= UmmaCfg::ACC_SLOTS;
     if (kv->umma) {
       // stage width: the largest multiple of 512 columns <= 2560 that divides K
@@ -1331,10 +1334,12 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
       std::vector<int> xmap_of;      // phase -> activation map index (-1: none)
       int x_cols_max = 0, stage_max = 0, n_sync = 1;
       // one weight matrix = one or more (sub-)phases: pieces of <= xcap columns (each staged once), a piece = full stages of kc
-      // columns plus, if kc does not divide it, ONE shorter tail stage per unit that re-uses the staged block
+      // columns plus, if kc does not divide it, ONE shorter tail stage per unit that re-uses the staged block.  K is walked in whole
+      // 512-column MMA groups: when 512 does not divide it (Llama-2-7B's down_proj, K = 11008) the last group's missing 64-column
+      // panels lie outside BOTH tensor maps (dims use the real K) and the TMA unit zero-fills them without reading memory
       auto add_matrix = [&](PhaseDesc d, const bf16* W) {
-        const int K = d.K;
-        d.ldx = K; d.rows = UmmaCfg::ROWS;
+        const int K_real = d.K, K = cdiv(d.K, 512) * 512;
+        d.ldx = K_real; d.rows = UmmaCfg::ROWS;
         int k0 = 0;
         while (k0 < K) {
           const int piece = (K - k0) < xcap ? (K - k0) : xcap;
@@ -1348,14 +1353,14 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
           if (tail_cols == 0) q.flags |= last_piece ? PHF_LAST : PHF_LOCAL_SYNC;
           else q.flags |= PHF_NO_SYNC;
           ph.push_back(q);
-          map_of.push_back(add_map(W, d.N, K, kc));
-          xmap_of.push_back(add_xmap(d.x_in, K, piece));
+          map_of.push_back(add_map(W, d.N, K_real, kc));
+          xmap_of.push_back(add_xmap(d.x_in, K_real, piece));
           if (tail_cols > 0) {
             PhaseDesc t = d;
             t.k_off = k0 + main_cols; t.K = tail_cols; t.kc = tail_cols; t.x_cols = 0; t.x_panel0 = main_cols / 64;
             t.flags = last_piece ? PHF_LAST : PHF_LOCAL_SYNC;
             ph.push_back(t);
-            map_of.push_back(add_map(W, d.N, K, tail_cols));
+            map_of.push_back(add_map(W, d.N, K_real, tail_cols));
             xmap_of.push_back(-1);
           }
           if (piece > x_cols_max) x_cols_max = piece;

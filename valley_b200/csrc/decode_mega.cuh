@@ -257,15 +257,20 @@ VLY_DEVINL void mega_attention_phase(const StepParams& p, const PhaseDesc& d, co
       *reinterpret_cast<float4*>(po + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
     if (lane == 0) p.part_ml[(size_t)bh * p.nsplit + split] = make_float2(m_run, l_run);
-    __threadfence();
+    // publish: every lane's partial stores, then ONE acq_rel atomic by lane 0 (release orders the warp's stores -- made
+    // cumulative by the __syncwarp -- before the count; acquire orders the merger's loads after it).  A separate membar.gl in
+    // every lane plus a relaxed atomic cost an extra L2 round trip on the phase's critical path.
     __syncwarp();
     int last = 0;
-    if (lane == 0) last = (atomicAdd(p.attn_counters + bh, 1u) == (unsigned)n_act - 1);
+    if (lane == 0) {
+      unsigned int old;
+      asm volatile("fence.acq_rel.gpu;\n\tatom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.attn_counters + bh) : "memory");
+      last = (old == (unsigned)n_act - 1);
+    }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {
       // ---- merge of the n_act (<= 128) partials by the warp that arrived last: lane s holds (max, sum) of splits s + 32 i.
       // The first batch of partial outputs is requested together with the (max, sum) pairs: one L2 round trip, not two.
-      __threadfence();
       const float* pb = p.part_o + (size_t)bh * p.nsplit * 128 + lane * 4;
       float4 v[8];
 #pragma unroll

@@ -58,9 +58,12 @@ SHAPE_7B_1L_V3 = ShapeSpec("shape-7b-1l-v3", 4096, 1, 32, 11008, vit_layers=2, p
 # intermediate_size = 7 x 512: the tcgen05 decode consumer (B = 2..4) walks down_proj as full 2560-column stages plus a 1024-column
 # tail stage; with VLY_UMMA_XC=512 as seven re-staged 512-column sub-phases
 TINY_UMMA = ShapeSpec("tiny-umma", 512, 2, 4, 3584, vocab_size=1032, vit_layers=2)
+# intermediate_size = 59 x 64 (not a multiple of 512, like Llama-2-7B's 11008): the last 512-column MMA group of down_proj has five
+# 64-column panels outside the tensor maps, zero-filled by the TMA unit
+TINY_UMMA_RAGGED = ShapeSpec("tiny-umma-ragged", 512, 2, 4, 3776, vocab_size=1032, vit_layers=2)
 
 SPECS = {s.name: s for s in (VALLEY2_7B, VALLEY_13B, TINY, TINY_WIDE, SHAPE_7B_1L, SHAPE_13B_1L, TINY_V2, TINY_V3, TINY_MAX,
-                             SHAPE_7B_1L_V3, TINY_UMMA)}
+                             SHAPE_7B_1L_V3, TINY_UMMA, TINY_UMMA_RAGGED)}
 
 
 def weight_shapes(spec: ShapeSpec, *, vision: bool = True, llm: bool = True) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
