@@ -283,13 +283,34 @@ static cudaError_t launch_ex(Kern kern, dim3 grid, dim3 block, size_t smem, cuda
 // ------------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------------
+// TMA-store epilogue (gemm_tc.cuh, TEPI): bf16 row-major outputs whose rows the TMA unit can address (16-byte aligned base and pitch)
+template <int EPI>
+static bool gemm_tepi_ok(const GemmParams& p) {
+  static const int env = getenv("VLY_GEMM_TEPI") ? atoi(getenv("VLY_GEMM_TEPI")) : 1;
+  if (!env) return false;
+  // (measured: it pays where the epilogue, not the main loop, sets the pace -- K <= 2048: ViT F = 64 10.24 -> 9.47 ms; with the
+  //  LLaMA widths, K = 4096 .. 13824, the 5-stage ring it needs costs more than the stores save: 13B prefill 46.6 -> 47.4 ms)
+  if (p.K > 2048 && env < 2) return false;
+  if (!(EPI == EPI_BIAS || EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU || EPI == EPI_BIAS_RES_STATS || EPI == EPI_RMS_SWIGLU)) return false;
+  if ((p.ldo & 7) || (reinterpret_cast<uintptr_t>(p.out) & 15)) return false;
+  if (EPI == EPI_BIAS_RES_STATS && ((p.ldr & 7) || (reinterpret_cast<uintptr_t>(p.residual) & 15))) return false;
+  return true;
+}
+
 template <int BN, int EPI>
 static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W, long long ldw, GemmParams p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  TRY(ensure_smem_attr(c->cfg.device, gemm_tc_kernel<BN, EPI>, Cfg::SMEM_BYTES));
-  CUtensorMap ta, tb;
+  constexpr bool kTepiMode = (EPI == EPI_BIAS || EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU || EPI == EPI_BIAS_RES_STATS || EPI == EPI_RMS_SWIGLU);
+  CUtensorMap ta, tb, to, tr;
   TRY(make_tmap_2d(c, &ta, A, p.K, p.M, lda * 2, 64, 128));
   TRY(make_tmap_2d(c, &tb, W, p.K, p.N, ldw * 2, 64, BN));
+  to = ta; tr = ta;                                        // (placeholders when the epilogue stores from registers)
+  const bool tepi = gemm_tepi_ok<EPI>(p);
+  if (tepi) {
+    const int n_out = (EPI == EPI_RMS_SWIGLU) ? p.N / 2 : p.N;
+    TRY(make_tmap_2d(c, &to, p.out, n_out, p.M, p.ldo * 2, 64, 32));
+    if (EPI == EPI_BIAS_RES_STATS) TRY(make_tmap_2d(c, &tr, p.residual, p.N, p.M, p.ldr * 2, 64, 32));
+  }
   p.num_m_tiles = cdiv(p.M, 128);
   p.num_n_tiles = cdiv(p.N, BN);
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -301,13 +322,11 @@ static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W
     const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
     const bool use_cg2 = cg2_env >= 0 ? (cg2_env == 1) : (pair_tiles >= 2 * pairs);
     if (use_cg2) {
-      TRY(ensure_smem_attr(c->cfg.device, gemm_tc_kernel<BN, EPI, true>, Cfg::SMEM_BYTES));
       CUtensorMap tb2;
       TRY(make_tmap_2d(c, &tb2, W, p.K, p.N, ldw * 2, 64, BN / 2));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2 * (pair_tiles < pairs ? pair_tiles : pairs));
       cfg.blockDim = dim3(Cfg::THREADS);
-      cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
       cfg.stream = st;
       cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -318,13 +337,35 @@ static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W
       attr[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = pdl_enabled() ? 2 : 1;
-      CK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true>, ta, tb2, p));
+      if constexpr (kTepiMode) {
+        if (tepi) {
+          constexpr int smem = gemm_smem_bytes<BN, true>();
+          TRY(ensure_smem_attr(c->cfg.device, gemm_tc_kernel<BN, EPI, true, true>, smem));
+          cfg.dynamicSmemBytes = smem;
+          CK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true, true>, ta, tb2, to, tr, p));
+          c->launches++;
+          return VLY_OK;
+        }
+      }
+      TRY(ensure_smem_attr(c->cfg.device, gemm_tc_kernel<BN, EPI, true, false>, Cfg::SMEM_BYTES));
+      cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      CK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true, false>, ta, tb2, to, tr, p));
       c->launches++;
       return VLY_OK;
     }
   }
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  CK(launch_ex(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, true, ta, tb, p));
+  if constexpr (kTepiMode && BN == 128) {
+    if (tepi) {
+      constexpr int smem = gemm_smem_bytes<BN, true>();
+      TRY(ensure_smem_attr(c->cfg.device, gemm_tc_kernel<BN, EPI, false, true>, smem));
+      CK(launch_ex(gemm_tc_kernel<BN, EPI, false, true>, dim3(grid), dim3(Cfg::THREADS), smem, st, true, ta, tb, to, tr, p));
+      c->launches++;
+      return VLY_OK;
+    }
+  }
+  TRY(ensure_smem_attr(c->cfg.device, gemm_tc_kernel<BN, EPI, false, false>, Cfg::SMEM_BYTES));
+  CK(launch_ex(gemm_tc_kernel<BN, EPI, false, false>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, true, ta, tb, to, tr, p));
   c->launches++;
   return VLY_OK;
 }

@@ -5,6 +5,13 @@
 //   warps 2..5  : epilogue -- tcgen05.ld the accumulator (one TMEM lane == one output row per thread),
 //                 apply the fused epilogue, store.  Two accumulator stages in TMEM so the epilogue
 //                 of tile i overlaps the main loop of tile i+1.
+//   TEPI = true : the bf16 output leaves through shared memory and TMA tensor stores, and the residual rows arrive by TMA loads:
+//                 a thread owns a ROW of the tile, so its 16-byte global stores / loads touched 32 different 128-byte lines per
+//                 warp instruction -- 32 LSU cycles each, ~4000 cycles per 128 x 256 tile for the stores alone, as long as the
+//                 main loop of a K = 1024 tile (ncu: tensor pipe 45-62 % active on the ViT's QKV / fc1 / out_proj GEMMs; more
+//                 epilogue warps made it worse).  Each epilogue warp stages 32 rows x 64 columns (4 KB, 128-byte swizzle:
+//                 conflict-free 16-byte shared stores) and one lane issues a cp.async.bulk.tensor store of the box; tile edges are
+//                 clipped by the TMA unit.
 //
 // Both operands are K-major, i.e. A is a row-major activation matrix and B is an nn.Linear weight
 // [out_features, in_features] exactly as HuggingFace stores it.
@@ -73,33 +80,60 @@ struct GemmCfg {
 };
 
 // x*sigmoid(1.702x) and x*sigmoid(x) on the fast MUFU path (ex2.approx + rcp.approx)
-VLY_DEVINL float quick_gelu_f(float v) { return __fdividef(v, 1.0f + fast_exp2(-2.4554669595930156f * v)); }
-VLY_DEVINL float silu_f(float v) { return __fdividef(v, 1.0f + fast_exp2(-1.4426950408889634f * v)); }
+// sigmoid(y) = 0.5 + 0.5 tanh(y / 2): ONE MUFU op (tanh.approx.f32, |rel err| ~ 2^-11, far below the bf16 rounding of the result)
+// instead of two (ex2 + rcp).  A 128 x 256 fc1 tile has 32768 activations per CTA: at 16 MUFU ops per clock per SM the
+// exp + reciprocal form alone took 4096 cycles -- the whole main loop of a K = 1024 tile.
+VLY_DEVINL float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+VLY_DEVINL float quick_gelu_f(float v) {   // v * sigmoid(1.702 v)
+  const float h = 0.5f * v;
+  return fmaf(h, tanh_approx(0.851f * v), h);
+}
+VLY_DEVINL float silu_f(float v) {         // v * sigmoid(v)
+  const float h = 0.5f * v;
+  return fmaf(h, tanh_approx(h), h);
+}
+
+// shared-memory footprint of a launch (TEPI: 5 ring stages of 32 KB + 4 warps x 3 staging boxes of 4 KB)
+template <int BN, bool TEPI>
+constexpr int gemm_smem_bytes() {
+  return TEPI ? 5 * 32768 + 4 * 3 * 4096 + 1024 + 256 + GemmCfg<BN>::VEC_BYTES : GemmCfg<BN>::SMEM_BYTES;
+}
 
 // CG2 = true: launched as clusters of 2 CTAs; the pair computes a 256 x BN tile with cta_group::2 MMAs (each CTA holds
 // 128 rows of A and BN/2 rows of B per stage and ends up with its own 128 output rows in its own TMEM).
-template <int BN, int EPI, bool CG2 = false>
+template <int BN, int EPI, bool CG2 = false, bool TEPI = false>
 __global__ void __launch_bounds__(192, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_o,
+               const __grid_constant__ CUtensorMap tma_r, const GemmParams p) {
+  static_assert(!TEPI || ((BN == 128 || CG2) && (EPI == EPI_BIAS || EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU || EPI == EPI_BIAS_RES_STATS ||
+                                                 EPI == EPI_RMS_SWIGLU)),
+                "TMA-store epilogue: 32 KB stages and a bf16 row-major output only");
   using Cfg = GemmCfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK;
   constexpr int B_ROWS = CG2 ? BN / 2 : BN;                      // rows of B this CTA stages
   constexpr int B_BYTES = B_ROWS * BK * 2;
   constexpr int STAGE_BYTES = Cfg::A_BYTES + B_BYTES;
-  constexpr int STAGES = CG2 ? 6 : Cfg::STAGES;                  // 32 KB stages in pair mode
+  constexpr int STAGES = TEPI ? 5 : (CG2 ? 6 : Cfg::STAGES);     // 32 KB stages in pair mode
   static_assert(STAGES * STAGE_BYTES <= Cfg::STAGES * Cfg::STAGE_BYTES, "pair-mode ring must fit the single-CTA budget");
+  constexpr int STG_BOX = 4096;                                  // staging box: 32 rows x 64 bf16 columns
+  constexpr int RING_END = TEPI ? STAGES * STAGE_BYTES + 4 * 3 * STG_BOX : Cfg::STAGES * Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_END);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* svec = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // [2][2][BN]
+  uint64_t* res_full_all = bars + 2 * STAGES + 5;                 // [4 epilogue warps][2]: residual boxes have landed (TEPI)
+  float* svec = reinterpret_cast<float*>(smem + RING_END + 256);   // [2][2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,6 +148,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if constexpr (TEPI) {
+      tma_prefetch_desc(&tma_o);
+      if constexpr (EPI == EPI_BIAS_RES_STATS) tma_prefetch_desc(&tma_r);
+      for (int i = 0; i < 8; ++i) mbar_init(&res_full_all[i], 1);
+    }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -204,6 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int r_in_tile = quad * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t res_ph = 0;        // TEPI: parity bits of this warp's two residual-box barriers
     pdl_wait();                 // residual rows / row statistics of the previous kernel are read below
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int m_step = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
@@ -225,8 +265,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       // residual rows do not depend on the MMA: issue every load of the tile before waiting for the accumulator
-      uint4 resv[(EPI == EPI_BIAS_RES_STATS) ? BN / 8 : 1];
-      if constexpr (EPI == EPI_BIAS_RES_STATS) {
+      // (TEPI: one lane starts the TMA loads of the first two 32 x 64 residual boxes of this warp's rows instead)
+      constexpr int STG_CPS = (EPI == EPI_RMS_SWIGLU) ? 4 : 2;            // 32-column accumulator chunks per 64-column output box
+      constexpr int STG_NSLAB = BN / 32 / STG_CPS;
+      uint8_t* stg = smem + STAGES * STAGE_BYTES + (warp - 2) * 3 * STG_BOX;
+      uint64_t* res_full = res_full_all + (warp - 2) * 2;
+      const int stg_row0 = m_blk * BM + quad * 32;
+      const int stg_col0 = (EPI == EPI_RMS_SWIGLU) ? (n_blk * BN) >> 1 : n_blk * BN;
+      if constexpr (TEPI && EPI == EPI_BIAS_RES_STATS) {
+        if (lane == 0) {
+#pragma unroll
+          for (int sl = 0; sl < 2 && sl < STG_NSLAB; ++sl) {
+            mbar_expect_tx(&res_full[sl], STG_BOX);
+            tma_load_2d(stg + sl * STG_BOX, &tma_r, &res_full[sl], stg_col0 + sl * 64, stg_row0);
+          }
+        }
+      }
+      uint4 resv[(EPI == EPI_BIAS_RES_STATS && !TEPI) ? BN / 8 : 1];
+      if constexpr (EPI == EPI_BIAS_RES_STATS && !TEPI) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n_blk * BN);
 #pragma unroll
         for (int j = 0; j < BN / 8; ++j)
@@ -272,6 +328,126 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           peer_row = (p.peer_frame_off + (long long)f * p.peer_frame_stride) * p.peer_tokens + (row - f * p.peer_tokens);
         }
       }
+      if constexpr (TEPI) {
+        // ---- output through shared memory + TMA tensor stores; residual through TMA loads (see the header) ----
+        constexpr bool kRes = (EPI == EPI_BIAS_RES_STATS);
+        const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + as * BN;
+        uint32_t rbuf[2][32];
+        __syncwarp();
+        tmem_ld_32x32(t_acc, rbuf[0]);
+#pragma unroll
+        for (int sl = 0; sl < STG_NSLAB; ++sl) {
+          uint4 rs[kRes ? 8 : 1];
+          if constexpr (kRes) {
+            mbar_wait(&res_full[sl & 1], (res_ph >> (sl & 1)) & 1u);
+            res_ph ^= 1u << (sl & 1);
+            const uint8_t* rrow = stg + (sl & 1) * STG_BOX + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rs[j] = *reinterpret_cast<const uint4*>(rrow + ((j ^ (lane & 7)) << 4));
+            __syncwarp();                                   // every lane has read the box: it may be refilled
+            if (lane == 0 && sl + 2 < STG_NSLAB) {
+              mbar_expect_tx(&res_full[sl & 1], STG_BOX);
+              tma_load_2d(stg + (sl & 1) * STG_BOX, &tma_r, &res_full[sl & 1], stg_col0 + (sl + 2) * 64, stg_row0);
+            }
+          }
+          uint4 o4[8];
+#pragma unroll
+          for (int cc = 0; cc < STG_CPS; ++cc) {
+            const int c = sl * STG_CPS + cc;
+            tmem_ld_wait();
+            __syncwarp();
+            if (c + 1 < BN / 32) tmem_ld_32x32(t_acc + (c + 1) * 32, rbuf[(c + 1) & 1]);
+            const int n0 = n_blk * BN + c * 32;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rbuf[c & 1][i]);
+            if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_RES_STATS) {
+              const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = b4[j];
+                v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+              }
+            }
+            if constexpr (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU) {
+              const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
+              const float4* c4 = reinterpret_cast<const float4*>(scol + c * 32);
+              const float nm = -mean * rstd;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = b4[j], cc4 = c4[j];
+                const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, cq[4] = {cc4.x, cc4.y, cc4.z, cc4.w};
+#pragma unroll
+                for (int t4 = 0; t4 < 4; ++t4) {
+                  float t = fmaf(rstd, v[4 * j + t4], fmaf(nm, cq[t4], bq[t4]));   // rstd*(acc - mean*colsum) + bias
+                  if constexpr (EPI == EPI_LN_BIAS_GELU) t = quick_gelu_f(t);
+                  v[4 * j + t4] = t;
+                }
+              }
+            }
+            if constexpr (EPI == EPI_RMS_SWIGLU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= rstd;
+              uint32_t ow[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a = silu_f(v[4 * j]) * v[4 * j + 1];
+                const float b = silu_f(v[4 * j + 2]) * v[4 * j + 3];
+                ow[j] = pack_bf16x2(a, b);
+              }
+              o4[cc * 2] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              o4[cc * 2 + 1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            } else if constexpr (kRes) {
+              // residual add, bf16 rounding, partial row statistics of the ROUNDED values
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rr = rs[cc * 4 + j];
+                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float a = v[j * 8 + t * 2] + bf16_lo(rw[t]);
+                  const float b = v[j * 8 + t * 2 + 1] + bf16_hi(rw[t]);
+                  ow[t] = pack_bf16x2(a, b);
+                  const float ar = bf16_lo(ow[t]), br = bf16_hi(ow[t]);
+                  st_sum += ar + br;
+                  st_sq += ar * ar + br * br;
+                }
+                o4[cc * 4 + j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              }
+              if (p.n_peers > 0 && row_ok && n0 < p.N) {   // compute + collective in one kernel: the tile is pushed to every rank as it retires
+                for (int q = 0; q < p.n_peers; ++q) {
+                  uint4* pp = reinterpret_cast<uint4*>(p.peer_out[q] + (size_t)peer_row * p.ldo + n0);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) pp[j] = o4[cc * 4 + j];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o4[cc * 4 + j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+          // the 32 x 64 box: row = lane, 16-byte chunk j at (j ^ (lane & 7)) -- the 128-byte swizzle the tensor map expects, and
+          // conflict-free for the warp's 16-byte stores.  Residual mode: ONE output box (boxes 0, 1 hold the residual ping-pong);
+          // otherwise two, alternating.
+          uint8_t* so = stg + (kRes ? 2 : (sl & 1)) * STG_BOX;
+          if (lane == 0) {                                    // the earlier store from this box has finished reading it
+            if constexpr (kRes) bulk_wait_group_read<0>();
+            else bulk_wait_group_read<1>();
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(so + lane * 128 + ((j ^ (lane & 7)) << 4)) = o4[j];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tma_o, so, stg_col0 + sl * 64, stg_row0);
+            bulk_commit_group();
+          }
+        }
+      } else {
       // one 32-column chunk: epilogue math + store
       auto process_chunk = [&](const uint32_t (&r)[32], const int c) {
         const int n0 = n_blk * BN + c * 32;
@@ -422,6 +598,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (c + 2 < BN / 32) tmem_ld_32x32(t_acc + (c + 2) * 32, ra);
         process_chunk(rb, c + 1);
       }
+      }
       __syncwarp();
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
@@ -436,6 +613,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           p.stats_out[(size_t)row * p.num_n_tiles + n_blk] = make_float2(st_sum, st_sq);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if constexpr (TEPI) {
+      if (lane == 0) bulk_wait_group_all();    // the staging boxes stay valid (and the stores complete) before the CTA retires
     }
   }
 
