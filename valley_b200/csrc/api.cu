@@ -823,6 +823,7 @@ static int launch_vit_attention(vly_ctx* c, const bf16* qkv, int F, bf16* out, c
   p.heads = g.vit_heads;
   p.D = D;
   p.ctx = out;
+  p.qkv = qkv;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
   {
     static long long* dbg = nullptr;

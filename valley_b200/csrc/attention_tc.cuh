@@ -33,6 +33,7 @@ struct VitAttnParams {
   int heads;                // 16
   int D;                    // 1024
   __nv_bfloat16* ctx;       // [F*tokens, D]
+  const __nv_bfloat16* qkv; // [F*tokens, 3D] (the tensor the TMA maps describe; the ping-pong kernel reads three single rows directly)
   float scale_log2e;        // head_dim^-0.5 * log2(e)
   long long* dbg;           // optional cycle counters (profiling aid)
 };
@@ -564,6 +565,10 @@ llama_prefill_attention_kernel(const __grid_constant__ CUtensorMap tma_q, const 
 //   is handled on CUDA cores -- one 64-wide dot product and one axpy per row -- which keeps the MMA shapes clean
 //   (N = 256, K = 256) and removes the 272-column padding.  K is reloaded for the next (frame, head) as soon as the
 //   item's last S-MMA retires, V when its last P V retires.
+//   warp 17              : the 257th QUERY row of every (frame, head) on CUDA cores, straight from the K / V tiles in shared
+//   memory (64 conflict-free 16-byte loads for the scores, 128 8-byte loads for P V per lane): a third 128-row query tile with
+//   ONE valid row cost a full trip through the S-MMA / softmax / P V / epilogue chain, and the chain's latency -- not MUFU or
+//   issue slots -- is what bounds this kernel.  Two tiles per item also pin query tile 0 to warpgroup A and tile 1 to B.
 // ============================================================================================
 struct VitAttnPPCfg {
   static constexpr int Q_BYTES = 128 * 128;
@@ -580,14 +585,15 @@ struct VitAttnPPCfg {
   // 227 KB is the hard limit: there is no room for an alignment slack, the kernel traps if the dynamic shared memory
   // window is not 1024-byte aligned (it is when the kernel has no static shared memory)
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
-  static constexpr int THREADS = 544;                      // warp 0 + two softmax warpgroups of 8 warps
+  static constexpr int THREADS = 576;                      // warp 0 + two softmax warpgroups of 8 warps + the last-row warp
+  static constexpr int TPI = 2;                            // 128-row query tiles per (frame, head): rows 0..255; row 256 -> warp 17
   static constexpr int TMEM_COLS = 512;
   static constexpr int O_OFF = 192;
 };
 static_assert(VitAttnPPCfg::SMEM_BYTES <= 232448, "ViT attention exceeds 227 KB of shared memory");
 
 // tma_q: 2D over qkv [F*257, 3D], box {64,128};  tma_x: same tensor, box {64,1}
-__global__ void __launch_bounds__(544, 1)
+__global__ void __launch_bounds__(576, 1)
 vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_x, const VitAttnParams p) {
   using C = VitAttnPPCfg;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -609,15 +615,16 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items_total = p.F * p.heads;
   const int my_items = (n_items_total > (int)blockIdx.x) ? (n_items_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int n_tiles = my_items * 3;
+  constexpr int TPI = C::TPI;
+  const int n_tiles = my_items * TPI;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_x);
     mbar_init(k_full, 1);
     mbar_init(v_full, 1);
-    mbar_init(k_done, 1);
-    mbar_init(v_done, 1);
+    mbar_init(k_done, 2);       // the item's last S-MMA has retired (tcgen05.commit) AND warp 17 has read K
+    mbar_init(v_done, 2);       // the item's last P V has retired AND warp 17 has read V
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
@@ -648,7 +655,7 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       const uint64_t desc_v = make_smem_desc_sw128(base_u32 + C::OFF_V, 16, 1024);
       uint32_t kf_ph = 0, vf_ph = 0, kd_ph = 0, vd_ph = 0, q_ph[2] = {0, 0}, p_ph[2] = {0, 0}, rf_ph[2] = {0, 0};
       long long w_vf = 0, w_pf = 0, w_vd = 0, w_rf = 0, w_kf = 0, w_qf = 0, w_kd = 0, x_mma = 0, x_tma = 0; const long long t_begin = clock64();
-      auto item_of = [&](int g) { return (int)blockIdx.x + (g / 3) * (int)gridDim.x; };
+      auto item_of = [&](int g) { return (int)blockIdx.x + (g / TPI) * (int)gridDim.x; };
       auto load_k = [&](int item, int par) {
         const int f = item / p.heads, h = item % p.heads, row0 = f * p.tokens;
         mbar_expect_tx(k_full, C::KV_BYTES);
@@ -663,7 +670,7 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       };
       auto back = [&](int t) {     // O = P V for tile t
         const int R = t & 1;
-        if (t % 3 == 0) {          // first tile of an item: its V must have landed
+        if (t % TPI == 0) {        // first tile of an item: its V must have landed
           { const long long tq_ = clock64(); mbar_wait(v_full, vf_ph); w_vf += clock64() - tq_; }
           vf_ph ^= 1;
         }
@@ -680,12 +687,12 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
           tc_mma_bf16(d_o, dp0 + uint64_t((j >> 2) * (128 * 128 / 16) + (j & 3) * 2), desc_v + uint64_t(j * (16 * 128 / 16)), idesc_pv, j != 0);
         tc_commit(&o_full[R]);
         x_mma += clock64() - tm_;
-        if (t % 3 == 2) tc_commit(v_done);      // every P V of the item has been issued
+        if (t % TPI == TPI - 1) tc_commit(v_done);      // every P V of the item has been issued
       };
       // Q tile + the 257th key / value rows of the (frame, head) travel together on the region's q_full barrier.  They are
       // issued one tile AHEAD: Q_R / X_R[parity] are free as soon as p_full of the region's previous tile was observed.
       auto issue_q = [&](int g) {
-        const int R = g & 1, qt = g % 3, item = item_of(g);
+        const int R = g & 1, qt = g % TPI, item = item_of(g);
         const int f = item / p.heads, h = item % p.heads, row0 = f * p.tokens;
         uint8_t* xr = smem + C::OFF_X + R * 384;       // kx: read before p_full; vx: read in the epilogue -> double buffered
         mbar_expect_tx(&q_full[R], C::Q_BYTES + 256);
@@ -697,13 +704,13 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       load_v(item_of(0), 0);
       issue_q(0);
       for (int g = 0; g < n_tiles; ++g) {
-        const int R = g & 1, qt = g % 3, item = item_of(g);
+        const int R = g & 1, qt = g % TPI, item = item_of(g);
         if (qt == 0 && g > 0) {
           // the previous item's last P V is still pending: issue it, then its V buffer can be refilled
           back(g - 1);
           { const long long tq_ = clock64(); mbar_wait(v_done, vd_ph); w_vd += clock64() - tq_; }
           vd_ph ^= 1;
-          load_v(item, (g / 3) & 1);
+          load_v(item, (g / TPI) & 1);
         }
         { const long long tq_ = clock64(); mbar_wait(&r_free[R], rf_ph[R] ^ 1); w_rf += clock64() - tq_; }     // region R (S/O columns, Q_R, P_R) released by the epilogue of tile g-2
         rf_ph[R] ^= 1;
@@ -722,12 +729,12 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
           tc_commit(&s_full[R]);
           x_mma += clock64() - tm_;
         }
-        if (qt == 2) {
+        if (qt == TPI - 1) {
           tc_commit(k_done);
           if (g + 1 < n_tiles) {                 // refill K for the next item while this item's softmax / P V run
             { const long long tq_ = clock64(); mbar_wait(k_done, kd_ph); w_kd += clock64() - tq_; }
             kd_ph ^= 1;
-            load_k(item_of(g + 1), ((g + 1) / 3) & 1);
+            load_k(item_of(g + 1), ((g + 1) / TPI) & 1);
           }
         }
         if (qt != 0 && g > 0) back(g - 1);       // (for qt == 0 it was issued above)
@@ -738,7 +745,7 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       mbar_wait(v_done, vd_ph);
       if (p.dbg) { long long* o = p.dbg + (size_t)blockIdx.x * 16; o[0] = clock64() - t_begin; o[1] = w_rf; o[2] = w_qf; o[3] = w_kf; o[4] = w_kd; o[5] = w_pf; o[6] = x_mma; o[7] = x_tma; }
     }
-  } else {
+  } else if (warp <= 16) {
     // ================= softmax + epilogue warpgroups: 8 warps each, TWO threads per query row =================
     // thread (row r, half hf) owns key columns [128*hf, 128*hf+128) of S; half 0 also owns the 257th key and the epilogue.
     const int R = (warp - 1) >> 3;           // 0: warps 1-8, 1: warps 9-16
@@ -754,7 +761,7 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
     __nv_bfloat16* xmax = reinterpret_cast<__nv_bfloat16*>(smem + C::OFF_XMAX) + R * 256;   // [2 halves][128]
     float* xsum = reinterpret_cast<float*>(smem + C::OFF_XSUM) + R * 128;                    // [128] (written by half 1)
     for (int g = R; g < n_tiles; g += 2) {
-      const int qt = g % 3, it = g / 3, item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int qt = g % TPI, it = g / TPI, item = (int)blockIdx.x + it * (int)gridDim.x;
       const int f = item / p.heads, h = item % p.heads;
       const int qrow = qt * 128 + r;
       const bool warp_active = (qt * 128 + quad * 32) < p.tokens;
@@ -881,6 +888,82 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       }
     }
     if (p.dbg && hf == 0 && r == 0) { long long* o = p.dbg + (size_t)blockIdx.x * 16 + 8 + R * 4; o[0] = clock64() - g_begin; o[1] = g_sf; o[2] = g_bar; o[3] = g_of; }
+  } else {
+    // ================= warp 17: query row 256 (the last token) of every item, on CUDA cores =================
+    // scores: lane l owns keys l + 32 i (i = 0..7) and the whole q row in registers; P V: half-warp hw owns keys 2 t + hw, lane
+    // (hl) owns head dims 4 hl .. 4 hl + 3.  fp32 throughout (the tile path rounds P to bf16 for the MMA).
+    pdl_wait();
+    const int hl = lane & 15, hw = lane >> 4;
+    const uint8_t* sK = smem + C::OFF_K;
+    const uint8_t* sV = smem + C::OFF_V;
+    uint32_t kf_ph = 0, vf_ph = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int f = item / p.heads, h = item % p.heads;
+      const __nv_bfloat16* xrow = p.qkv + ((size_t)f * p.tokens + 256) * (3 * (size_t)p.D) + h * 64;
+      uint4 qw[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) qw[c] = __ldg(reinterpret_cast<const uint4*>(xrow) + c);
+      auto dot8 = [](const uint4 a, const uint4 b) {
+        return bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
+               bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+      };
+      float s_x = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) s_x += dot8(qw[c], __ldg(reinterpret_cast<const uint4*>(xrow + p.D) + c));
+      const uint2 vxw = __ldg(reinterpret_cast<const uint2*>(xrow + 2 * p.D) + hl);
+      mbar_wait(k_full, kf_ph);
+      kf_ph ^= 1;
+      float sc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = lane + 32 * i;
+        const uint8_t* kr = sK + (row >> 7) * (128 * 128) + (row & 127) * 128;
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a += dot8(qw[c], *reinterpret_cast<const uint4*>(kr + ((c ^ (row & 7)) << 4)));
+        sc[i] = a;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(k_done);            // K may be refilled (together with the last S-MMA's commit)
+      float mx = s_x;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, sc[i]);
+      mx = warp_max(mx);
+      const float mb = mx * p.scale_log2e;
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sc[i] = fast_exp2(fmaf(sc[i], p.scale_log2e, -mb));
+        part += sc[i];
+      }
+      const float p_x = fast_exp2(fmaf(s_x, p.scale_log2e, -mb));
+      const float inv = __frcp_rn(warp_sum(part) + p_x);
+      mbar_wait(v_full, vf_ph);
+      vf_ph ^= 1;
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll 8
+        for (int t = 0; t < 16; ++t) {
+          const int j = 32 * i + 2 * t + hw;           // key; its weight sits in sc[i] of lane j & 31
+          const float pj = __shfl_sync(0xffffffffu, sc[i], 2 * t + hw);
+          const uint8_t* vr = sV + (j >> 7) * (128 * 128) + (j & 127) * 128;
+          const uint2 w = *reinterpret_cast<const uint2*>(vr + ((((hl >> 1) ^ (j & 7)) << 4) | ((hl & 1) << 3)));
+          o0 = fmaf(pj, bf16_lo(w.x), o0); o1 = fmaf(pj, bf16_hi(w.x), o1);
+          o2 = fmaf(pj, bf16_lo(w.y), o2); o3 = fmaf(pj, bf16_hi(w.y), o3);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_done);            // V may be refilled (together with the last P V's commit)
+      o0 += __shfl_xor_sync(0xffffffffu, o0, 16); o1 += __shfl_xor_sync(0xffffffffu, o1, 16);
+      o2 += __shfl_xor_sync(0xffffffffu, o2, 16); o3 += __shfl_xor_sync(0xffffffffu, o3, 16);
+      if (hw == 0) {
+        o0 = fmaf(p_x, bf16_lo(vxw.x), o0) * inv; o1 = fmaf(p_x, bf16_hi(vxw.x), o1) * inv;
+        o2 = fmaf(p_x, bf16_lo(vxw.y), o2) * inv; o3 = fmaf(p_x, bf16_hi(vxw.y), o3) * inv;
+        *reinterpret_cast<uint2*>(p.ctx + ((size_t)f * p.tokens + 256) * p.D + h * 64 + hl * 4) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      }
+    }
   }
 
   tc_fence_before();
