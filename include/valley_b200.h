@@ -147,6 +147,9 @@ int vly_embed_splice(vly_ctx* ctx, const int64_t* ids_dev, const int32_t* src_ma
 int vly_kv_create(vly_ctx* ctx, int batch, int max_seq, vly_kv** out);
 void vly_kv_destroy(vly_kv* kv);
 int vly_kv_seq_len(vly_kv* kv, int* out_len);   /* host-visible length (syncs the kv's stream state) */
+/* which kernel a decode step of this context launches ("decode_step_umma_kernel<4>", "decode_step_kernel<1>", ...): written,
+ * NUL-terminated, into name (capacity cap).  For reports (bench.py names the kernel its roofline describes); no GPU work. */
+int vly_kv_decode_kernel(vly_kv* kv, char* name, int cap);
 int vly_kv_reset(vly_kv* kv, void* stream);
 /* HF's 2-D attention_mask (HF masking_utils: the padding mask is AND-ed into the causal mask; build_inputs /
  * tokenizer(padding=True) pad on the LEFT, valley_model.py:249-254 passes the mask through): mask_dev [B, len] uint8 on the

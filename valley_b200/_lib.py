@@ -70,6 +70,7 @@ SIGNATURES = {
     "vly_build_splice_map": (_i, [_p(_i64), _i, _i, _i, _p(VlyTokens), _p(C.c_int32), _p(C.c_int32)]),
     "vly_embed_splice": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "vly_kv_create": (_i, [_vp, _i, _i, _p(_vp)]),
+    "vly_kv_decode_kernel": (_i, [_vp, C.c_char_p, _i]),
     "vly_kv_destroy": (None, [_vp]),
     "vly_kv_seq_len": (_i, [_vp, _p(_i)]),
     "vly_kv_reset": (_i, [_vp, _vp]),

@@ -1513,6 +1513,14 @@ extern "C" int vly_kv_create(vly_ctx* c, int batch, int max_seq, vly_kv** out) {
   return VLY_OK;
 }
 
+extern "C" int vly_kv_decode_kernel(vly_kv* kv, char* name, int cap) {
+  if (!kv || !name || cap <= 0) return fail(VLY_ERR_INVALID, "vly_kv_decode_kernel: bad argument");
+  const int bmax = kv->B <= 1 ? 1 : (kv->B <= 2 ? 2 : 4);
+  if (decode_mode() == 2 && kv->B <= 4) snprintf(name, (size_t)cap, "%s<%d>", kv->umma ? "decode_step_umma_kernel" : "decode_step_kernel", bmax);
+  else snprintf(name, (size_t)cap, "%s", decode_mode() == 0 ? "per-op decode kernels (generation 1)" : "per-op TMA-ring decode kernels");
+  return VLY_OK;
+}
+
 extern "C" void vly_kv_destroy(vly_kv* kv) {
   if (!kv) return;
   cudaSetDevice(kv->ctx->cfg.device);

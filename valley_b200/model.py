@@ -131,6 +131,12 @@ class ValleyKVCache:
         check(self._model._lib.vly_kv_seq_len(self._h, C.byref(n)))
         return n.value
 
+    def decode_kernel(self) -> str:
+        """name of the kernel a decode step of this cache launches (for reports)"""
+        buf = C.create_string_buffer(96)
+        check(self._model._lib.vly_kv_decode_kernel(self._h, buf, 96))
+        return buf.value.decode()
+
     def __len__(self):
         return self._model.config.num_hidden_layers
 
