@@ -43,8 +43,8 @@ from valley_b200 import synthetic as syn  # noqa: E402
 
 GFLOP_PER_FRAME = {-2: 155.29, -1: 162.02}
 # committed ncu --set full captures of decode_step_kernel, per (model, batch): dram bytes per launch (profiles/)
-NCU_DECODE = {("valley2-7b", 1): "prof_mega_r01_final_summary.csv", ("valley-13b", 4): "prof_mega_r02_13b_b4_summary.csv",
-              ("valley2-7b", 4): "prof_mega_r02_7b_b4_summary.csv", ("valley-13b", 1): "prof_mega_r02_13b_b1_summary.csv"}
+NCU_DECODE = {("valley2-7b", 1): "prof_mega_r02_7b_b1_summary.csv", ("valley-13b", 4): "prof_mega_r02_13b_b4_summary.csv",
+              ("valley-13b", 1): "prof_mega_r02_13b_b1_summary.csv"}
 
 
 def prompt_len(n_frames):

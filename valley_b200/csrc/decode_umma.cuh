@@ -188,12 +188,15 @@ __global__ void __launch_bounds__(576, 1) decode_step_umma_kernel(const StepPara
             tma_load_3d(xsw, reinterpret_cast<const CUtensorMap*>(d.xmap), x_bar, 0, 0, d.k_off >> 6);
           }
           mbar_wait(x_bar, xph);
-          if (norm) {
+          // RMSNorm statistics: the row scale is applied in the epilogue, so the MMA issuers (warps 1, 2) start on the raw block at
+          // once; warps 3..16 sum the squares and meet the epilogue warp on their own named barrier
+          if (norm && warp > U::ISSUERS) {
             float sq[BMAX];
 #pragma unroll
             for (int b = 0; b < BMAX; ++b) sq[b] = 0.f;
             const int chunks = d.x_cols >> 3;
-            for (int c = ct; c < chunks; c += MegaCfg::CONSUMERS) {
+            constexpr int NT = (16 - U::ISSUERS) * 32;
+            for (int c = ct - U::ISSUERS * 32; c < chunks; c += NT) {
               const uint8_t* src = xsw + (size_t)(c >> 3) * 1024;
 #pragma unroll
               for (int b = 0; b < BMAX; ++b) {
@@ -216,14 +219,15 @@ __global__ void __launch_bounds__(576, 1) decode_step_umma_kernel(const StepPara
           }
         }
         xph ^= 1;
-        if (norm) {
-          asm volatile("bar.sync 2, 544;" ::: "memory");
-          if (!is_fin && ct < BMAX) {
+        if (norm && warp > U::ISSUERS) {
+          constexpr int NB = (17 - U::ISSUERS) * 32;          // warps 3..17
+          asm volatile("bar.sync 3, %0;" ::"n"(NB) : "memory");
+          if (is_fin && lane < BMAX) {
             float t = 0.f;
-            for (int w = 0; w < 16; ++w) t += wred[w * BMAX + ct];
-            rstd_s[ct] = rsqrtf(t / d.K + p.eps);
+            for (int w = U::ISSUERS; w < 16; ++w) t += wred[w * BMAX + lane];
+            rstd_s[lane] = rsqrtf(t / d.K + p.eps);
           }
-          asm volatile("bar.sync 2, 544;" ::: "memory");
+          if (is_fin) __syncwarp();
         }
       }
       t_stage += clock64() - t0;
