@@ -105,6 +105,8 @@ def load():
             "(nvcc, sm_100a). valley_b200 has no CPU or PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if not hasattr(lib, name) and os.environ.get("VLY_LIB_PATH"):
+            continue                     # an OLDER build loaded on purpose for a same-box A/B (tools/): it may predate an entry point
         fn = getattr(lib, name)          # AttributeError here == the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
     _lib = lib
