@@ -155,10 +155,24 @@ VLY_DEVINL void mega_attention_phase(const StepParams& p, const PhaseDesc& d, co
   const int len = pos + 1;
   // (the phase lasts as long as its busiest warp: rounds x keys per item -- e.g. 2400 32-key items on 2368 warps are 2 rounds of
   //  32 keys, the same work as 4800 16-key items are 3 rounds of 16)
+  // (round 2b) item size = any multiple of 16 keys: the one that minimises rounds x keys, and among equals the one with the fewest
+  // rounds -- every round ends in a publish (fence + atomic) and every extra item is one more partial for the merge: e.g. B = 4,
+  // 40 heads, 590 keys on 2368 warps = one round of 48-key items (three passes) instead of three rounds of 16-key items: at that
+  // length the phase's tail (waiting for the mergers) shrank from 22 to 6 us per layer.  (Software-pipelining the K/V loads
+  // across the passes was tried too: the extra live registers spill -- 96 is the cap at 576 threads -- and cost more than the
+  // overlapped round trip saved.)
   const int n_warps = 16 * (int)gridDim.x;
-  const int it16 = p.B * p.nH * ((len + 15) >> 4), it32 = p.B * p.nH * ((len + 31) >> 5);
-  const int w16 = ((it16 + n_warps - 1) / n_warps) * 16, w32 = ((it32 + n_warps - 1) / n_warps) * 32;
-  const int ikeys = p.attn_ikeys ? p.attn_ikeys : ((w16 < w32 || (w16 == w32 && it16 <= n_warps)) ? 16 : 32);   // tie: one pass if everything fits one round
+  int ikeys = p.attn_ikeys;
+  if (ikeys == 0) {
+    int best = 1 << 30;
+    for (int m = 16; m <= 256; m += 16) {
+      const int items_m = p.B * p.nH * ((len + m - 1) / m);
+      const int rounds = (items_m + n_warps - 1) / n_warps;
+      const int cost = rounds * m * 4 + rounds;               // keys first, then rounds
+      if (cost < best) { best = cost; ikeys = m; }
+      if (rounds == 1 && m >= 32) break;                      // larger items only add keys from here on
+    }
+  }
   const int n_act = (len + ikeys - 1) / ikeys;
   const int items = p.B * p.nH * n_act;
   const int hl = lane & 15, hw = lane >> 4;
@@ -168,7 +182,7 @@ VLY_DEVINL void mega_attention_phase(const StepParams& p, const PhaseDesc& d, co
     const int k0 = split * ikeys, nk = min(len - k0, ikeys);
     const __nv_bfloat16* kb = d.kcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
     const __nv_bfloat16* vb = d.vcache + ((size_t)bh * p.Smax + k0) * 128 + hl * 8;
-    const uint32_t kbits = __ldg(p.key_bits + (size_t)b * p.mask_words + (k0 >> 5)) >> (k0 & 31);   // one mask bit per cache position
+    const uint32_t* kbw = p.key_bits + (size_t)b * p.mask_words;                                  // one mask bit per cache position
     float qf[8];
     {
       const uint4 w = ldcg_v4(p.q + (size_t)b * p.H + h * 128 + hl * 8);
@@ -179,6 +193,7 @@ VLY_DEVINL void mega_attention_phase(const StepParams& p, const PhaseDesc& d, co
     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int kk0 = 0; kk0 < nk; kk0 += 16) {
+      const uint32_t kbits = __ldg(kbw + ((k0 + kk0) >> 5)) >> ((k0 + kk0) & 31);                // the 16 mask bits of this pass
       uint4 kw[8], vw[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -194,6 +209,7 @@ VLY_DEVINL void mega_attention_phase(const StepParams& p, const PhaseDesc& d, co
         sc[j] = qf[0] * bf16_lo(w.x) + qf[1] * bf16_hi(w.x) + qf[2] * bf16_lo(w.y) + qf[3] * bf16_hi(w.y) +
                 qf[4] * bf16_lo(w.z) + qf[5] * bf16_hi(w.z) + qf[6] * bf16_lo(w.w) + qf[7] * bf16_hi(w.w);
       }
+
       // transposing reduction over the 16 lanes of the half-warp: afterwards sc[0] = the full dot product of key
       // kk0 + 2 * (hl >> 1) + hw (held twice: lanes hl and hl ^ 1)
 #pragma unroll
@@ -210,7 +226,7 @@ VLY_DEVINL void mega_attention_phase(const StepParams& p, const PhaseDesc& d, co
       }
       sc[0] += __shfl_xor_sync(0xffffffffu, sc[0], 1);
       const int my_key = kk0 + 2 * (hl >> 1) + hw;
-      const bool valid = my_key < nk && ((kbits >> my_key) & 1u);
+      const bool valid = my_key < nk && ((kbits >> (my_key - kk0)) & 1u);
       const float s_my = valid ? sc[0] * p.scale_log2e : -INFINITY;
       float mx = s_my;
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
