@@ -1870,7 +1870,7 @@ static int launch_decode_mega(vly_ctx* c, vly_kv* kv, cudaStream_t st) {
   p.n_grid_syncs = kv->n_grid_syncs;
   {
     static const int env_ik = getenv("VLY_ATTN_IKEYS") ? atoi(getenv("VLY_ATTN_IKEYS")) : 0;
-    p.attn_ikeys = (env_ik == 16 || env_ik == 32) ? env_ik : 0;
+    p.attn_ikeys = (env_ik >= 16 && env_ik <= 256 && env_ik % 16 == 0) ? env_ik : 0;
   }
   p.sample = kv->d_sample;
   {

@@ -145,33 +145,25 @@ VLY_DEVINL void grid_sync_consumers(unsigned int* counter, unsigned int target, 
 // (A CTA-per-(sequence, head) variant with a shared-memory merge was measured at 13B, B = 4: slower -- one SM cannot keep enough
 //  K/V loads in flight from registers; spreading every head over all SMs wins despite the global-memory merge.)
 VLY_DEVINL void mega_attention_phase(const StepParams& p, const PhaseDesc& d, const int cw, const int lane, const int pos) {
-  // ------------------------------ attention: one warp per (sequence, head, 32-key split) ------------------------------
+  // ------------------------------ attention: one warp per (sequence, head, key split) ------------------------------
   // A half-warp covers one key row (16 lanes x 16 bytes = 128 head dims); a pass handles 16 keys (8 per half-warp): all 8 K
   // and 8 V rows of a lane are requested up front (one L2 / HBM round trip), scores are reduced with a transposing shuffle
-  // tree (8 instead of 32 shuffles), softmax runs online in registers across the two passes of an item, P.V accumulates per
+  // tree (8 instead of 32 shuffles), softmax runs online in registers across the passes of an item, P.V accumulates per
   // lane over its 8 head dims.  Items are dealt warp-major over the SMs so one layer's K/V is pulled by every SM at once.
-  // Item size: with few (sequence, head, 16-key) items -- short contexts, B = 1 -- every item gets its own warp and a single
-  // round trip to the cache; otherwise 32 keys per item (two passes) halve the partials the merge has to read.
   const int len = pos + 1;
-  // (the phase lasts as long as its busiest warp: rounds x keys per item -- e.g. 2400 32-key items on 2368 warps are 2 rounds of
-  //  32 keys, the same work as 4800 16-key items are 3 rounds of 16)
-  // (round 2b) item size = any multiple of 16 keys: the one that minimises rounds x keys, and among equals the one with the fewest
-  // rounds -- every round ends in a publish (fence + atomic) and every extra item is one more partial for the merge: e.g. B = 4,
-  // 40 heads, 590 keys on 2368 warps = one round of 48-key items (three passes) instead of three rounds of 16-key items: at that
-  // length the phase's tail (waiting for the mergers) shrank from 22 to 6 us per layer.  (Software-pipelining the K/V loads
-  // across the passes was tried too: the extra live registers spill -- 96 is the cap at 576 threads -- and cost more than the
-  // overlapped round trip saved.)
+  // Item size = a multiple of 16 keys (one 16-key pass per 16).  Measured at B = 4, 40 heads (profiles/decode_ab_r02.txt, calls 25-26):
+  // what costs is the NUMBER of items -- every item ends in a publish (partial stores, fence, atomic) and is one more partial
+  // for the merge, ~8 us of shared-resource time per "round" of 2368 items -- while a pass adds ~3 us to a warp's serial chain:
+  //   461 keys: 2400 32-key items 23 us | 4640 16-key items 30 us;   591 keys: 2080 48-key items 26 us | 5920 16-key items 48 us.
+  // So: 16 keys if every 16-key item finds its own warp (B = 1), else the smallest multiple of 16 >= 32 whose item count fits the
+  // warps (5 % overflow into a second, nearly empty round costs less than a third pass for everybody).
   const int n_warps = 16 * (int)gridDim.x;
   int ikeys = p.attn_ikeys;
   if (ikeys == 0) {
-    int best = 1 << 30;
-    for (int m = 16; m <= 256; m += 16) {
-      const int items_m = p.B * p.nH * ((len + m - 1) / m);
-      const int rounds = (items_m + n_warps - 1) / n_warps;
-      const int cost = rounds * m * 4 + rounds;               // keys first, then rounds
-      if (cost < best) { best = cost; ikeys = m; }
-      if (rounds == 1 && m >= 32) break;                      // larger items only add keys from here on
-    }
+    if (p.B * p.nH * ((len + 15) >> 4) <= n_warps) ikeys = 16;
+    else
+      for (ikeys = 32; ikeys < 256; ikeys += 16)
+        if (p.B * p.nH * ((len + ikeys - 1) / ikeys) <= n_warps + n_warps / 20) break;
   }
   const int n_act = (len + ikeys - 1) / ikeys;
   const int items = p.B * p.nH * n_act;
