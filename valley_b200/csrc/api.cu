@@ -290,7 +290,9 @@ static bool gemm_tepi_ok(const GemmParams& p) {
   if (!env) return false;
   // (measured: it pays where the epilogue, not the main loop, sets the pace -- K <= 2048: ViT F = 64 10.24 -> 9.47 ms; with the
   //  LLaMA widths, K = 4096 .. 13824, the 5-stage ring it needs costs more than the stores save: 13B prefill 46.6 -> 47.4 ms)
-  if (p.K > 2048 && env < 2) return false;
+  // ... except the residual epilogue of a LONG K = 4096 GEMM with few column tiles (the ViT's fc2 at >= 48 frames: 9.59 -> 9.20 ms at
+  // 64 frames), where the row-wise residual loads + stores still rival the main loop
+  if (p.K > 2048 && env < 2 && !(EPI == EPI_BIAS_RES_STATS && p.K <= 4096 && p.M >= 12000)) return false;
   if (!(EPI == EPI_BIAS || EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU || EPI == EPI_BIAS_RES_STATS || EPI == EPI_RMS_SWIGLU)) return false;
   if ((p.ldo & 7) || (reinterpret_cast<uintptr_t>(p.out) & 15)) return false;
   if (EPI == EPI_BIAS_RES_STATS && ((p.ldr & 7) || (reinterpret_cast<uintptr_t>(p.residual) & 15))) return false;
@@ -320,7 +322,9 @@ static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W
     static const int cg2_env = getenv("VLY_GEMM_CG2") ? atoi(getenv("VLY_GEMM_CG2")) : -1;
     const int pairs = c->num_sms / 2;
     const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
-    const bool use_cg2 = cg2_env >= 0 ? (cg2_env == 1) : (pair_tiles >= 2 * pairs);
+    // (measured: pairs win from one full wave of pair tiles on -- ViT, 32 frames: 5.23 -> 5.10 ms; below that -- 16 frames, 68 tiles of
+    //  the N = 1024 GEMMs -- the single-CTA tiles spread better: 3.05 vs 3.09 ms)
+    const bool use_cg2 = cg2_env >= 0 ? (cg2_env == 1) : (pair_tiles >= pairs);
     if (use_cg2) {
       CUtensorMap tb2;
       TRY(make_tmap_2d(c, &tb2, W, p.K, p.N, ldw * 2, 64, BN / 2));
