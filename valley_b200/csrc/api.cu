@@ -324,7 +324,9 @@ static int launch_gemm_t(vly_ctx* c, const bf16* A, long long lda, const bf16* W
     const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
     // (measured: pairs win from one full wave of pair tiles on -- ViT, 32 frames: 5.23 -> 5.10 ms; below that -- 16 frames, 68 tiles of
     //  the N = 1024 GEMMs -- the single-CTA tiles spread better: 3.05 vs 3.09 ms)
-    const bool use_cg2 = cg2_env >= 0 ? (cg2_env == 1) : (pair_tiles >= pairs);
+    //  An odd, small number of 128-row tiles wastes the pair's second half (M = 333: 3 tiles -> 4): those wait for two full waves.
+    const bool small_odd = (p.num_m_tiles & 1) && p.num_m_tiles < 7;
+    const bool use_cg2 = cg2_env >= 0 ? (cg2_env == 1) : (pair_tiles >= (small_odd ? 2 : 1) * pairs);
     if (use_cg2) {
       CUtensorMap tb2;
       TRY(make_tmap_2d(c, &tb2, W, p.K, p.N, ldw * 2, 64, BN / 2));
