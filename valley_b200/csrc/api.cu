@@ -388,8 +388,23 @@ static inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
 // exchange row statistics compute it ONCE per (N, M) and pass it around.
 static inline int pick_bn_m(const vly_ctx* c, int N, int M) {
   if (N % 256 != 0) return 128;
+  static const int env_bn = getenv("VLY_GEMM_BN") ? atoi(getenv("VLY_GEMM_BN")) : 0;      // 128 / 256: force (A/B measurements)
+  if (env_bn == 128 || env_bn == 256) return env_bn;
   const long long t256 = (long long)cdiv(M, 128) * (N / 256), t128 = 2 * t256;
   if (t256 >= 3LL * c->num_sms) return 256;            // many rounds: the last one matters little, operand reuse matters more
+  {
+    // CTA pairs (256 x 256 tiles, launch_gemm_t) sustain ~1.5x the rate of single 128 x 128 tiles (ncu, LLaMA-13B prefill: 1.22 vs
+    // 0.82 PFLOP/s), so a reasonably full pair launch beats a perfectly full 128-wide one: M = 1332, N = 5120 -- 120 pair tiles on 74
+    // pairs, 11 of 12 row tiles real = 0.74 -- took 3.2 ms off the 13B prefill (47.9 -> 44.7).  Below ~0.7 (8 ViT frames: 0.69) the
+    // narrow tiles stay.
+    const int mt = cdiv(M, 128), pairs = c->num_sms / 2;
+    const long long pt = (long long)cdiv(mt, 2) * (N / 256);
+    const bool small_odd = (mt & 1) && mt < 7;
+    if (pt >= (small_odd ? 2 : 1) * pairs) {
+      const double e_pair = (double)pt / ((double)cdiv(pt, pairs) * pairs) * ((double)mt / (2.0 * cdiv(mt, 2)));
+      if (e_pair >= 0.70) return 256;
+    }
+  }
   const double e256 = (double)t256 / ((double)cdiv(t256, c->num_sms) * c->num_sms);
   const double e128 = (double)t128 / ((double)cdiv(t128, c->num_sms) * c->num_sms);
   return (e128 > e256 * 1.05) ? 128 : 256;
