@@ -348,7 +348,8 @@ def main():
         "parallelism": f"dp{a.gpus}" + ("" if a.gpus <= 1 else " (frames dealt round-robin over ranks -> every rank needs remote frames; frame features gathered by the "
                                         "last ViT GEMM epilogue via NVLink peer stores; LLM replicated, each rank decodes its own videos)"),
         "l2": f"inputs larger than L2 ({2 * (spec.num_hidden_layers * (4 * spec.hidden_size ** 2 + 3 * spec.hidden_size * spec.intermediate_size) + spec.vocab_size * spec.hidden_size) / 1e9:.1f} GB "
-              "of weights stream per decode step; ViT weights 606 MB)"}
+              "of weights stream per decode step; ViT weights 606 MB)",
+        "stopping": f"eos stopping disabled (eos_token_id=None): every sequence runs exactly {N_NEW} decode steps on every path"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -440,7 +441,7 @@ def main():
     def step_device():
         if world > 1:
             return vdist.generate_sharded(model, ids_dev, px_dev, n_videos, T, N_NEW, fused=fused, interleaved=True)
-        return model.generate(input_ids=ids_dev, images=px_dev.view(B, T, 3, 224, 224), max_new_tokens=N_NEW)[:, S:]
+        return model.generate(input_ids=ids_dev, images=px_dev.view(B, T, 3, 224, 224), max_new_tokens=N_NEW, eos_token_id=None)[:, S:]
 
     def step_e2e():
         px = px_local_host.cuda(non_blocking=True)
@@ -448,7 +449,7 @@ def main():
         if world > 1:
             out = vdist.generate_sharded(model, ids, px, n_videos, T, N_NEW, fused=fused, interleaved=True)
         else:
-            out = model.generate(input_ids=ids, images=px.view(B, T, 3, 224, 224), max_new_tokens=N_NEW)[:, S:]
+            out = model.generate(input_ids=ids, images=px.view(B, T, 3, 224, 224), max_new_tokens=N_NEW, eos_token_id=None)[:, S:]
         return out.cpu()
 
     if os.environ.get("VLY_BENCH_PROFILE"):
@@ -475,7 +476,7 @@ def main():
         # this rank's tokens from the sharded path vs a single-GPU run of the same videos (all of their frames encoded locally)
         toks_sharded = step_device()
         own_px = px_all.view(n_videos, T, 3, 224, 224)[vlo:vhi].cuda()
-        toks_single = model.generate(input_ids=ids_dev, images=own_px, max_new_tokens=N_NEW)[:, S:]
+        toks_single = model.generate(input_ids=ids_dev, images=own_px, max_new_tokens=N_NEW, eos_token_id=None)[:, S:]
         tm = torch.tensor([1 if torch.equal(toks_sharded, toks_single) else 0], device="cuda")
         dist.all_reduce(tm, op=dist.ReduceOp.MIN)
         fused.check()
@@ -590,7 +591,7 @@ def main():
             ids7 = syn.make_prompt_ids(s7, 1, 8, 0).cuda()
             px7 = syn.make_pixels(1, 8, 0, dtype=torch.float16).cuda()
             S7 = ids7.shape[1]
-            ms7, l7, _ = timed(lambda: m7.generate(input_ids=ids7, images=px7, max_new_tokens=128)[:, S7:], 3, 2, m7)
+            ms7, l7, _ = timed(lambda: m7.generate(input_ids=ids7, images=px7, max_new_tokens=128, eos_token_id=None)[:, S7:], 3, 2, m7)
             d7, smid7, p7, _, k7 = llm_only(m7, s7, 1, 8, 128)
             b7 = decode_bytes_per_step(s7, 1, smid7)
             tr7, src7 = ncu_traffic("valley2-7b", 1)
