@@ -706,11 +706,11 @@ def test_production_shapes_one_layer(spec_name, B):
     torch.cuda.empty_cache()
 
 
-def _decode_parity(spec_name, B, n=8, seed=0):
+def _decode_parity(spec_name, B, n=8, seed=0, len_a=20, len_b=11):
     spec, sd, m = get(spec_name, seed)
     cfg, tok = Hh.oracle_cfg(spec), Hh.oracle_tok(spec)
     T = 2
-    ids, px = syn.make_prompt_ids(spec, B, T, 0, len_a=20, len_b=11), syn.make_pixels(B, T, 0)
+    ids, px = syn.make_prompt_ids(spec, B, T, 0, len_a=len_a, len_b=len_b), syn.make_pixels(B, T, 0)
     with torch.no_grad():
         r_tok, r_log = O.greedy_generate(sd, cfg, tok, ids, px, n, return_logits=True)
     m.logits_all_positions = False
@@ -746,6 +746,15 @@ def test_tcgen05_decode_consumer_full_and_tail_stages(B):
     tail stage per work unit of down_proj (two sub-phases on one staged activation block); prefill + 8 teacher-forced steps +
     free-running ids vs the oracle.  B = 1 on the same model runs decode_step_kernel<1> (the reference point)."""
     _decode_parity("tiny-umma", B)
+
+
+@pytest.mark.parametrize("len_a,len_b", [(230, 120), (400, 250)])
+def test_decode_attention_multi_pass_items_at_production_head_count(len_a, len_b):
+    """B = 4 sequences x 40 heads (one LLaMA-13B-wide layer) at contexts of ~610 and ~910 keys: more 16- / 32-key items than the
+    2368 warps of the decode kernel, so the attention phase runs 48- / 64-key items (3 - 4 passes per warp, mask bits fetched per
+    pass, up to 5 % of the items in a second round) -- the regime the headline request spends its second half in.  Prefill logits,
+    8 teacher-forced decode steps and free-running ids vs the oracle."""
+    _decode_parity("shape-13b-1l", 4, len_a=len_a, len_b=len_b)
 
 
 def _decode_parity_subprocess(env, calls):
