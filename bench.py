@@ -14,7 +14,9 @@ mm_projector -> splice -> LLaMA prefill -> greedy decode (one persistent kernel 
 `value` = generated tokens/s over whole steps, inputs resident in HBM; `e2e` = the same through
 ValleyLlamaForCausalLM.generate() (N>1: dist.generate_sharded) from pinned HOST buffers, H2D of pixels + ids and D2H of the token
 ids inside the timed region.  The two halves of the metric -- ViT frames/s and steady-state decode tokens/s -- are timed
-separately on the device and reported with their roofline fractions (`roofline` = decode_step_kernel, HBM; `roofline_vit`).
+separately on the device and reported with their roofline fractions (`roofline` = the persistent decode-step kernel the library
+launches for this batch -- named in `roofline.kernel` --, HBM; `roofline_vit`).  Every generate call passes eos_token_id=None: exactly
+`--new-tokens` decode steps run on every path.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model valley-13b|valley2-7b|tiny] ...
   N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...

@@ -143,7 +143,7 @@ def test_valley2_7b_full_depth_prefill_and_decode_vs_fp32_oracle():
 
 def test_valley_13b_b4_full_depth_prefill_and_decode_vs_fp32_oracle():
     """BASELINE config 3 (the metric's model): valley-13b (40 layers), 4 videos x 8 frames; the decode steps run
-    decode_step_kernel<4> (tensor-core consumers), the prefill the CTA-pair GEMMs at M = 1332."""
+    decode_step_umma_kernel<4> (tcgen05 consumer), the prefill the CTA-pair GEMMs at M = 1332."""
     free = torch.cuda.mem_get_info()[0]
     if free < 120e9:
         pytest.skip(f"needs ~110 GB of device memory for the fp32 oracle weights + the packed model (free: {free / 1e9:.0f} GB)")
