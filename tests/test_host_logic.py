@@ -334,3 +334,40 @@ def test_splice_plan_and_oracle_match_the_reference_on_fuzzed_rows():
             with pytest.raises(IndexError):
                 oracle_map(row, T, tok)
     assert seen["map"] >= 40 and seen["ValueError"] >= 100 and seen["IndexError"] >= 10 and seen["plain"] >= 50
+
+
+def test_load_video_directory_of_images_branch_equals_the_reference(tmp_path):
+    """load_video's directory branch (data_util.py:282-302: rglob, linspace selection, PIL open, optional square resize,
+    CLIPImageProcessor) -- host code, no GPU.  The fixture (oracle/make_golden_imgdir.py, written from the LIVE reference) holds
+    the SHA-256 of every frame the reference produced, keyed by file name: the directory order is whatever the file system
+    returns, so the check is per selected file."""
+    import hashlib
+    import importlib.util
+    import numpy as np
+    from valley_b200 import video
+    here = os.path.dirname(__file__)
+    g = torch.load(os.path.join(here, "golden", "ref_imgdir.pt"))
+    spec = importlib.util.spec_from_file_location("make_golden_imgdir_images", os.path.join(os.path.dirname(here), "oracle", "make_golden_imgdir.py"))
+    src = open(spec.origin).read()
+    ns = {}
+    # only the image generator of the script (its module-level imports need /root/reference): the function is self-contained
+    start, end = src.index("def make_images"), src.index("def sha(")
+    from PIL import Image
+    exec(src[start:end], {"np": np, "Image": Image, "os": os, "SIZES": g["sizes"]}, ns)
+    for method, sizes, seed0 in (("centercrop", g["sizes"], 500), ("resize", g["same"], 700)):
+        d = tmp_path / method
+        d.mkdir()
+        names = ns["make_images"](str(d), sizes, seed0)
+        for n_fixed in sorted({3, len(names)}):
+            picked = video.select_image_dir_frames(str(d), "fixed", n_fixed)
+            assert len(picked) == n_fixed and {p.name for p in picked} <= set(names)
+            out = video.load_image_dir(str(d), None, "fixed", n_fixed, method)
+            assert out.shape == (n_fixed, 3, 224, 224) and out.dtype == torch.float32
+            for k, p in enumerate(picked):
+                want = g["frames"][(method, p.name)]
+                assert torch.equal(out[k].flatten()[::997], want["sample"]), (method, p.name)
+                assert hashlib.sha256(out[k].contiguous().numpy().tobytes()).hexdigest() == want["sha256"], (method, p.name)
+    with pytest.raises(ValueError, match="Input folder is not support this frame mode"):
+        video.load_image_dir(str(tmp_path / "centercrop"), None, "fps")
+    with pytest.raises(ValueError, match='Frame mode is only support "fps" or "fixed"'):
+        video.load_image_dir(str(tmp_path / "centercrop"), None, "other")

@@ -13,6 +13,7 @@ eager / CPU fallback for any op on the path.
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 import types
 from typing import Iterable, List, Optional, Tuple, Union
@@ -823,8 +824,11 @@ class ValleyLlamaForCausalLM(_ModuleSurface):
             images = video.permute(1, 0, 2, 3).unsqueeze(0).half().to(self.device)
         else:
             from . import video as _video
-            reader = self.video_reader_factory(str(video))
-            images = _video.load_video(self, reader, "fixed", 8, dtype=torch.float16).unsqueeze(0)      # [1,T,3,224,224]
+            if os.path.isdir(str(video)):              # load_video's directory-of-images branch (data_util.py:282-302)
+                images = _video.load_image_dir(str(video), getattr(self, "image_processor", None)).unsqueeze(0).half().to(self.device)
+            else:
+                reader = self.video_reader_factory(str(video))
+                images = _video.load_video(self, reader, "fixed", 8, dtype=torch.float16).unsqueeze(0)      # [1,T,3,224,224]
         gen_kwargs = dict(gen_kwargs)
         if "attention_mask" not in gen_kwargs and getattr(inputs, "attention_mask", None) is not None:
             am = torch.as_tensor(inputs.attention_mask)

@@ -74,3 +74,36 @@ def load_video(model, reader, frame_mode: str = "fixed", fixed_frame_number: int
     frames = reader.get_batch(idx)
     frames = torch.as_tensor(np.asarray(frames) if not torch.is_tensor(frames) else frames)
     return preprocess_frames(model, frames.to(torch.uint8), dtype)
+
+
+# ---- the directory-of-images branch of load_video (data_util.py:282-302): CPU work, library code on both sides ----
+def select_image_dir_frames(path, frame_mode: str = "fixed", fixed_frame_number: int = 8):
+    """The files ``load_video`` opens for a directory: ``Path(path).rglob('*')`` in directory order (data_util.py:283), then
+    ``np.linspace(0, n - 1, fixed_frame_number)`` of them (:284-286); 'fps' and anything else raise as the reference does (:287-290)."""
+    from pathlib import Path
+    files = list(Path(path).rglob('*'))
+    if frame_mode == 'fixed':
+        return [files[i] for i in np.linspace(0, len(files) - 1, fixed_frame_number).astype(np.int_)]
+    if frame_mode == 'fps':
+        raise ValueError('Input folder is not support this frame mode')
+    raise ValueError('Frame mode is only support "fps" or "fixed"')
+
+
+def load_image_dir(path, image_processor=None, frame_mode: str = "fixed", fixed_frame_number: int = 8,
+                   frame_process_method: str = "centercrop") -> torch.Tensor:
+    """``load_video(path_to_a_directory_of_frames, image_processer, ...)`` (data_util.py:282-302) -> [T,3,224,224] float32 on the
+    host, FRAMES FIRST (the reference permutes to [3,T,...] and every caller permutes back).  Same calls as the reference: PIL
+    ``Image.open``, the optional square resize of ``frame_process_method='resize'`` (torchvision's Resize on a PIL image ==
+    ``Image.resize(..., BILINEAR)``), then the HF ``CLIPImageProcessor.preprocess`` (bicubic shortest-edge 224, centre crop,
+    1/255, CLIP mean/std).  ``image_processor=None`` builds the default ``CLIPImageProcessor()`` -- the reference would fail with
+    ``None.preprocess`` there (its ``completion`` never passes one)."""
+    from PIL import Image
+    frames = [Image.open(str(f)) for f in select_image_dir_frames(path, frame_mode, fixed_frame_number)]
+    if frame_process_method == 'resize':
+        m = min(frames[0].size)
+        frames = [f.resize((m, m), Image.BILINEAR) for f in frames]
+    if image_processor is None:
+        from transformers import CLIPImageProcessor
+        image_processor = CLIPImageProcessor()
+    return image_processor.preprocess(frames, return_tensors='pt')['pixel_values']
+
