@@ -371,3 +371,26 @@ def test_load_video_directory_of_images_branch_equals_the_reference(tmp_path):
         video.load_image_dir(str(tmp_path / "centercrop"), None, "fps")
     with pytest.raises(ValueError, match='Frame mode is only support "fps" or "fixed"'):
         video.load_image_dir(str(tmp_path / "centercrop"), None, "other")
+
+
+def test_keywords_stopping_criteria_matches_the_reference_semantics():
+    """valley/util/data_util.py:40-56: the FIRST call only records the prompt length (the first generated token is never tested
+    alone), later calls decode row 0 of output_ids[:, start_len:] and stop on any keyword.  Pure host logic."""
+    from valley_b200.model import KeywordsStoppingCriteria
+
+    class Tok:
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return ["".join(chr(int(t)) for t in row) for row in ids]
+
+    prompt = torch.tensor([[ord(c) for c in "ab"]])
+    crit = KeywordsStoppingCriteria(["###"], Tok(), prompt)
+    grow = lambda s: torch.tensor([[ord(c) for c in "ab" + s]])
+    assert crit(grow("###")) is False                 # first call: start_len recorded, nothing tested (the reference's quirk)
+    assert crit.start_len == 2
+    assert crit(grow("x#")) is False
+    assert crit(grow("x##")) is False
+    assert crit(grow("x###")) is True
+    assert crit(grow("###y"), scores=None) is True
+    two = KeywordsStoppingCriteria(["STOP", "\n\n"], Tok(), prompt)
+    two(grow(""))
+    assert two(grow("abc\n\n")) is True and two(grow("abc\n")) is False
