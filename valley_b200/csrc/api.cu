@@ -295,7 +295,9 @@ static bool gemm_tepi_ok(const GemmParams& p) {
   if (p.K > 2048 && env < 2 && !(EPI == EPI_BIAS_RES_STATS && p.K <= 4096 && p.M >= 12000)) return false;
   // The GEMM that also pushes its tiles to the peers (fused all-gather) keeps the register-store epilogue: that combination is the one
   // verified bit-identical to NCCL on 2 AND 8 GPUs.  With the staged epilogue it was bit-identical on 2 GPUs, but the one 8-GPU
-  // run taken with it reported a mismatch (profiles/bench_r02_n8_tepi_gather_mismatch.json) -- not understood yet, so not used.
+  // run taken with it reported a mismatch (profiles/bench_r02_n8_tepi_gather_mismatch.json).  Suspected: the residual-box
+  // refill in the staged epilogue is issued before the ld.shared of that box are known to have retired; behind 7 peers' NVLink stores
+  // they can still be queued when the TMA write lands.  To be fixed and re-verified on 8 GPUs before this is switched on.
   if (p.n_peers > 0 && env < 2) return false;
   if (!(EPI == EPI_BIAS || EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU || EPI == EPI_BIAS_RES_STATS || EPI == EPI_RMS_SWIGLU)) return false;
   if ((p.ldo & 7) || (reinterpret_cast<uintptr_t>(p.out) & 15)) return false;
